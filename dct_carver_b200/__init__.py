@@ -1,0 +1,280 @@
+"""dct_carver_b200 — B200-native DCT-Carver energy hot path.
+
+Thin ctypes mirror of the C ABI in include/dctc.h (the product is the CUDA library, not this file).
+Names follow the reference: EnergyParameters (src/render.h:9-18), blocksize / edges / textures
+(src/main.h:12-22).  There is no CPU fallback: if libdctc.so is missing or no CUDA device is present,
+loading / context creation raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdctc.so")
+
+OK = 0
+ERR_INVALID, ERR_BLOCKSIZE, ERR_NOMEM, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
+KERNEL_AUTO, KERNEL_FP32_TILE, KERNEL_FP32_MARCH, KERNEL_TC_SPLIT = 0, 1, 2, 3
+
+# every symbol include/dctc.h declares (tests check that the library exports exactly these)
+ABI_SYMBOLS = [
+    "dctc_create", "dctc_destroy", "dctc_set_params", "dctc_set_kernel", "dctc_last_cuda_error", "dctc_strerror",
+    "dctc_version", "dctc_device_count", "dctc_stream", "dctc_launch_count",
+    "dctc_energy_full", "dctc_energy_full_dev", "dctc_energy_batch_dev", "dctc_energy_band_dev", "dctc_energy_batch",
+    "dctc_carver_load", "dctc_carver_width", "dctc_carver_height", "dctc_carver_energy", "dctc_carve_and_update",
+    "dctc_carver_image", "dctc_carver_resize_width", "dctc_pixel_energy",
+    "dctc_synth_fill_dev", "dctc_synth_byte",
+    "dctc_dev_alloc", "dctc_dev_free", "dctc_host_alloc_pinned", "dctc_host_free_pinned", "dctc_memcpy_h2d",
+    "dctc_memcpy_d2h", "dctc_memset_dev", "dctc_sync", "dctc_timer_begin", "dctc_timer_end",
+]
+
+
+class EnergyParameters(C.Structure):
+    """Bit-for-bit the reference's EnergyParameters (src/render.h:9-18)."""
+    _fields_ = [("edges", C.c_float), ("textures", C.c_float), ("blocksize", C.c_int),
+                ("ip", C.POINTER(C.c_int)), ("w", C.POINTER(C.c_double)), ("data", C.POINTER(C.POINTER(C.c_double)))]
+
+
+class CarverEnergyParams(C.Structure):
+    _fields_ = [("base", EnergyParameters), ("gpu", C.c_void_p)]
+
+
+class DctcError(RuntimeError):
+    def __init__(self, status, what=""):
+        self.status = status
+        msg = "%s failed: %d" % (what, status)
+        try:
+            msg += " (%s)" % lib().dctc_strerror(status).decode()
+        except Exception:
+            pass
+        super().__init__(msg)
+
+
+_lib = None
+
+
+def lib():
+    """Loads libdctc.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("dct_carver_b200: %s is missing — run `python -m dct_carver_b200.build` "
+                          "(needs nvcc). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32, u32, f32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_float
+    sig = {
+        "dctc_create": (i32, [C.POINTER(vp), i32]),
+        "dctc_destroy": (None, [vp]),
+        "dctc_set_params": (i32, [vp, C.POINTER(EnergyParameters)]),
+        "dctc_set_kernel": (i32, [vp, i32]),
+        "dctc_last_cuda_error": (i32, [vp]),
+        "dctc_strerror": (C.c_char_p, [i32]),
+        "dctc_version": (i32, []),
+        "dctc_device_count": (i32, []),
+        "dctc_stream": (vp, [vp]),
+        "dctc_launch_count": (C.c_ulonglong, [vp]),
+        "dctc_energy_full": (i32, [vp, vp, i32, i32, i32, sz, vp]),
+        "dctc_energy_full_dev": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, i32]),
+        "dctc_energy_batch_dev": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, vp, sz, sz, i32]),
+        "dctc_energy_band_dev": (i32, [vp, vp, i32, i32, i32, sz, vp, i32, sz, vp, i32, sz, vp, sz, i32]),
+        "dctc_energy_batch": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, vp, sz]),
+        "dctc_carver_load": (i32, [vp, vp, i32, i32, i32, sz]),
+        "dctc_carver_width": (i32, [vp]),
+        "dctc_carver_height": (i32, [vp]),
+        "dctc_carver_energy": (i32, [vp, vp]),
+        "dctc_carve_and_update": (i32, [vp, vp, vp, vp, vp]),
+        "dctc_carver_image": (i32, [vp, vp]),
+        "dctc_carver_resize_width": (i32, [vp, i32, vp]),
+        "dctc_pixel_energy": (f32, [i32, i32, i32, i32, vp, vp]),
+        "dctc_synth_fill_dev": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, u32, i32, i32, i32]),
+        "dctc_synth_byte": (C.c_uint8, [u32, u32, u32, u32, u32, i32]),
+        "dctc_dev_alloc": (i32, [vp, C.POINTER(vp), sz]),
+        "dctc_dev_free": (i32, [vp, vp]),
+        "dctc_host_alloc_pinned": (i32, [C.POINTER(vp), sz]),
+        "dctc_host_free_pinned": (i32, [vp]),
+        "dctc_memcpy_h2d": (i32, [vp, vp, vp, sz]),
+        "dctc_memcpy_d2h": (i32, [vp, vp, vp, sz]),
+        "dctc_memset_dev": (i32, [vp, vp, i32, sz]),
+        "dctc_sync": (i32, [vp]),
+        "dctc_timer_begin": (i32, [vp]),
+        "dctc_timer_end": (i32, [vp, C.POINTER(f32)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _check(status, what):
+    if status != OK:
+        raise DctcError(status, what)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pinned_array(shape, dtype):
+    """numpy array over cudaMallocHost memory (kept alive by the returned array's base)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _check(lib().dctc_host_alloc_pinned(C.byref(p), n), "dctc_host_alloc_pinned")
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[id(buf)] = (buf, p.value)
+    return arr
+
+
+_PINNED = {}
+
+
+class Context:
+    """One GPU context (one caller at a time, like the reference's single-threaded callback)."""
+
+    def __init__(self, device=0, blocksize=8, edges=0.5, textures=0.5, kernel=KERNEL_AUTO):
+        self._h = C.c_void_p()
+        _check(lib().dctc_create(C.byref(self._h), device), "dctc_create")
+        self.device = device
+        self.set_params(blocksize, edges, textures)
+        if kernel != KERNEL_AUTO:
+            self.set_kernel(kernel)
+
+    # -- parameters ------------------------------------------------------------------------------------
+    def set_params(self, blocksize, edges, textures):
+        p = EnergyParameters(edges=edges, textures=textures, blocksize=blocksize)
+        _check(lib().dctc_set_params(self._h, C.byref(p)), "dctc_set_params")
+        self.blocksize, self.edges, self.textures = blocksize, edges, textures
+
+    def set_kernel(self, kernel):
+        _check(lib().dctc_set_kernel(self._h, kernel), "dctc_set_kernel")
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launches(self):
+        return int(lib().dctc_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().dctc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- K1 ---------------------------------------------------------------------------------------------
+    def energy_full(self, img):
+        """img: uint8 array [h, w] or [h, w, channels] (C-contiguous rows) -> float32 [h, w]."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8:
+            raise TypeError("image must be uint8")
+        if img.ndim == 2:
+            img = img[:, :, None]
+        img = np.ascontiguousarray(img)
+        h, w, ch = img.shape
+        out = np.empty((h, w), np.float32)
+        _check(lib().dctc_energy_full(self._h, _ptr(img), w, h, ch, w * ch, _ptr(out)), "dctc_energy_full")
+        return out
+
+    def energy_batch(self, imgs, out=None):
+        """imgs: uint8 [n, h, w, ch] host array (pinned for full speed) -> float32 [n, h, w]."""
+        n, h, w, ch = imgs.shape
+        if out is None:
+            out = np.empty((n, h, w), np.float32)
+        _check(lib().dctc_energy_batch(self._h, _ptr(imgs), n, h * w * ch, w, h, ch, w * ch, _ptr(out), h * w),
+               "dctc_energy_batch")
+        return out
+
+    # -- device memory helpers ----------------------------------------------------------------------------
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().dctc_dev_alloc(self._h, C.byref(p), nbytes), "dctc_dev_alloc")
+        return p.value
+
+    def dev_free(self, p):
+        _check(lib().dctc_dev_free(self._h, C.c_void_p(p)), "dctc_dev_free")
+
+    def h2d(self, d_ptr, arr):
+        arr = np.ascontiguousarray(arr)
+        _check(lib().dctc_memcpy_h2d(self._h, C.c_void_p(d_ptr), _ptr(arr), arr.nbytes), "dctc_memcpy_h2d")
+
+    def d2h(self, arr, d_ptr):
+        _check(lib().dctc_memcpy_d2h(self._h, _ptr(arr), C.c_void_p(d_ptr), arr.nbytes), "dctc_memcpy_d2h")
+
+    def sync(self):
+        _check(lib().dctc_sync(self._h), "dctc_sync")
+
+    def timer_begin(self):
+        _check(lib().dctc_timer_begin(self._h), "dctc_timer_begin")
+
+    def timer_end(self):
+        ms = C.c_float()
+        _check(lib().dctc_timer_end(self._h, C.byref(ms)), "dctc_timer_end")
+        return ms.value
+
+    def synth_fill_dev(self, d_img, n_frames, frame_stride, w, h, ch, pitch, seed, pattern=0, first_frame=0, y_offset=0):
+        _check(lib().dctc_synth_fill_dev(self._h, C.c_void_p(d_img), n_frames, frame_stride, w, h, ch, pitch, seed,
+                                         pattern, first_frame, y_offset), "dctc_synth_fill_dev")
+
+    def energy_batch_dev(self, d_imgs, n, frame_stride, w, h, ch, pitch, d_out, out_frame_stride, out_pitch, sync=False):
+        _check(lib().dctc_energy_batch_dev(self._h, C.c_void_p(d_imgs), n, frame_stride, w, h, ch, pitch,
+                                           C.c_void_p(d_out), out_frame_stride, out_pitch, int(sync)),
+               "dctc_energy_batch_dev")
+
+    def energy_band_dev(self, d_band, w, rows, ch, pitch, d_top, top_rows, top_pitch, d_bot, bot_rows, bot_pitch, d_out,
+                        out_pitch, sync=False):
+        _check(lib().dctc_energy_band_dev(self._h, C.c_void_p(d_band), w, rows, ch, pitch,
+                                          C.c_void_p(d_top) if d_top else None, top_rows, top_pitch,
+                                          C.c_void_p(d_bot) if d_bot else None, bot_rows, bot_pitch,
+                                          C.c_void_p(d_out), out_pitch, int(sync)), "dctc_energy_band_dev")
+
+    # -- K2 carver session ----------------------------------------------------------------------------------
+    def carver_load(self, img):
+        img = np.asarray(img)
+        if img.ndim == 2:
+            img = img[:, :, None]
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w, ch = img.shape
+        _check(lib().dctc_carver_load(self._h, _ptr(img), w, h, ch, w * ch), "dctc_carver_load")
+        self._carver_ch = ch
+
+    def carver_size(self):
+        return lib().dctc_carver_width(self._h), lib().dctc_carver_height(self._h)
+
+    def carver_energy(self):
+        w, h = self.carver_size()
+        out = np.empty((h, w), np.float32)
+        _check(lib().dctc_carver_energy(self._h, _ptr(out)), "dctc_carver_energy")
+        return out
+
+    def carver_image(self):
+        w, h = self.carver_size()
+        out = np.empty((h, w, self._carver_ch), np.uint8)
+        _check(lib().dctc_carver_image(self._h, _ptr(out)), "dctc_carver_image")
+        return out
+
+    def carve_and_update(self, seam_x, want_band=True):
+        """Removes one vertical seam; returns (band_values, xmin, xmax) like liblqr's update_emap would visit."""
+        w, h = self.carver_size()
+        seam = np.ascontiguousarray(seam_x, dtype=np.int32)
+        if seam.shape != (h,):
+            raise ValueError("seam must have one column per row")
+        xmin = np.empty(h, np.int32)
+        xmax = np.empty(h, np.int32)
+        band = np.empty(h * 4 * (self.blocksize // 2), np.float32) if want_band else None
+        _check(lib().dctc_carve_and_update(self._h, _ptr(seam), _ptr(band) if want_band else None, _ptr(xmin),
+                                           _ptr(xmax)), "dctc_carve_and_update")
+        if want_band:
+            n = int(np.maximum(xmax - xmin + 1, 0).sum())
+            band = band[:n]
+        return band, xmin, xmax

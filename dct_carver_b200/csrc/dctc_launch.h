@@ -1,0 +1,48 @@
+// Internal: kernel launchers and the context layout shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include "../../include/dctc.h"
+
+struct DctcK1Args;
+
+cudaError_t dctc_launch_k1_tile(const DctcK1Args& a, int blocksize, int n_frames, bool uniform, cudaStream_t stream);
+cudaError_t dctc_launch_synth(uint8_t* d_img, int n_frames, size_t frame_stride, int w, int h, int channels,
+                              size_t pitch, uint32_t seed, int pattern, int first_frame, int y_offset,
+                              cudaStream_t stream);
+
+constexpr int DCTC_SLOTS = 3;
+
+struct dctc_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // compute
+    cudaStream_t s_in = nullptr;        // H2D
+    cudaStream_t s_out = nullptr;       // D2H
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_in[DCTC_SLOTS] = {}, ev_k[DCTC_SLOTS] = {}, ev_out[DCTC_SLOTS] = {};
+    float edges = 0.5f, textures = 0.5f;  // defaults src/main.c:30-33
+    int blocksize = 8;
+    int kernel = DCTC_KERNEL_AUTO;
+    int last_cuda = 0;
+    unsigned long long launches = 0;
+    // staging slots of the host-buffer API
+    uint8_t* d_in[DCTC_SLOTS] = {};
+    float* d_out[DCTC_SLOTS] = {};
+    size_t d_in_cap[DCTC_SLOTS] = {}, d_out_cap[DCTC_SLOTS] = {};
+    // carver session (K2)
+    uint8_t* c_img = nullptr;      // device image, pitch c_pitch, compacted in place per seam
+    float* c_en = nullptr;         // device energy, pitch c_w0 floats
+    float* c_m = nullptr;          // cumulative map of the seam DP
+    int* c_seam = nullptr;         // h entries
+    int* c_band = nullptr;         // 2*h entries: xmin, xmax
+    float* c_band_vals = nullptr;  // packed band values
+    float* h_mirror = nullptr;     // host mirror of the energy map (pinned)
+    int* h_band = nullptr;         // pinned 2*h
+    int c_w0 = 0, c_w = 0, c_h = 0, c_ch = 0;
+    size_t c_pitch = 0;
+    bool mirror_valid = false;
+};
+
+int dctc_fail_cuda(dctc_context* ctx, cudaError_t e);
+void dctc_carver_release(dctc_context* ctx);

@@ -1,0 +1,178 @@
+/* dctc.h — C ABI of the B200-native DCT-Carver energy hot path.
+ *
+ * This is the drop-in boundary for ONE path of avivrosenberg/dct-carver: the per-pixel block-DCT energy
+ * map that the plug-in registers with liblqr as a custom energy function.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference tree).  Plain C: pointers and sizes
+ * only, no C++/torch types.  All compute runs in hand-written CUDA kernels for sm_100a
+ * (dct_carver_b200/csrc); there is NO CPU fallback: without a CUDA device every compute call returns
+ * DCTC_ERR_NO_DEVICE / DCTC_ERR_CUDA.
+ *
+ * Threading: one caller per context (the reference's callback is single-threaded and non re-entrant,
+ * src/render.c:140,154).  Use one context per GPU / stream.
+ */
+#ifndef DCTC_H
+#define DCTC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCTC_VERSION 1
+
+/* status codes (the reference has no error channel: bad blocksize -> error()+untransformed data,
+ * src/dct.c:89-92; OOM -> exit(1), src/fft2d/alloc.c:5-10.  Here every batch call returns int.) */
+enum {
+    DCTC_OK = 0,
+    DCTC_ERR_INVALID = -1,    /* NULL pointer, non-positive size, channels not in 1..4, pitch too small */
+    DCTC_ERR_BLOCKSIZE = -2,  /* blocksize not in {2,4,8,16}  (src/dct.c:77-93, UI combo src/interface.c:281) */
+    DCTC_ERR_NOMEM = -3,      /* cudaMalloc / cudaMallocHost failed */
+    DCTC_ERR_CUDA = -4,       /* a CUDA call failed; see dctc_last_cuda_error() */
+    DCTC_ERR_NO_DEVICE = -5,  /* no usable CUDA device */
+    DCTC_ERR_STATE = -6,      /* carver call without a loaded image / seam outside the current width */
+    DCTC_ERR_UNSUPPORTED = -7 /* requested kernel variant does not exist for this block size */
+};
+
+/* The reference's operator state, src/render.h:9-18, filled at src/render.c:296-305.
+ * Layout is kept bit-for-bit so a caller's existing struct can be passed as is.  ip / w / data are the
+ * Ooura scratch areas of the CPU path; the GPU path ignores them (scratch lives in registers/shared memory)
+ * and never frees caller memory (ownership: src/render.c:413-416). */
+typedef struct DctcEnergyParameters_ {
+    float edges;
+    float textures;
+    int blocksize;
+    int *ip;
+    double *w;
+    double **data;
+} DctcEnergyParameters;
+
+typedef struct dctc_context dctc_context;
+
+/* Superset handed to liblqr as extra_data (src/render.c:314-315): the prefix IS EnergyParameters, so the
+ * reference's own dct_pixel_energy could still read it; the tail carries the GPU context. */
+typedef struct DctcCarverEnergyParams_ {
+    DctcEnergyParameters base;
+    dctc_context *gpu;
+} DctcCarverEnergyParams;
+
+/* kernel selection for block size 8 (other block sizes always use the FP32 CUDA-core kernel) */
+enum {
+    DCTC_KERNEL_AUTO = 0,
+    DCTC_KERNEL_FP32_TILE = 1,   /* generic shared-memory tile kernel, all block sizes */
+    DCTC_KERNEL_FP32_MARCH = 2,  /* b=8 register-sliding column march */
+    DCTC_KERNEL_TC_SPLIT = 3     /* b=8 tcgen05 Toeplitz GEMM, fp16 hi/lo split operands, fp32 accumulate */
+};
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` with its own stream.  Replaces the scratch allocation of
+ * src/render.c:296-305 (alloc_1d_int / alloc_1d_double / alloc_2d_double). */
+int dctc_create(dctc_context **ctx, int device);
+/* Frees device buffers, pinned staging and the stream.  Counterpart of the frees at src/render.c:413-416. */
+void dctc_destroy(dctc_context *ctx);
+/* edges / textures / blocksize as PlugInVals carries them (src/main.h:12-22, src/main.c:151-153). */
+int dctc_set_params(dctc_context *ctx, const DctcEnergyParameters *params);
+int dctc_set_kernel(dctc_context *ctx, int kernel);
+int dctc_last_cuda_error(const dctc_context *ctx);
+const char *dctc_strerror(int status);
+int dctc_version(void);
+/* number of CUDA devices visible, or a negative status */
+int dctc_device_count(void);
+/* CUDA stream of the context as an opaque handle (cudaStream_t) */
+void *dctc_stream(dctc_context *ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+unsigned long long dctc_launch_count(const dctc_context *ctx);
+
+/* ---- K1: full energy map ----------------------------------------------------------------------------
+ * Replaces liblqr's build_emap loop "for y<h for x<w: en = dct_pixel_energy(x,y,w,h,rw,extra)"
+ * (callback src/render.c:134-157; dctNxN src/dct.c:77-94; weighted_max_dct_correlation src/dct.c:96-110)
+ * over the interleaved 8-bit buffer that lqr_carver_new() receives (src/render.c:310-312), with the
+ * LQR_ER_LUMA reader fused in.  out[y*w+x] is the gfloat the callback would return. */
+int dctc_energy_full(dctc_context *ctx, const uint8_t *img, int w, int h, int channels, size_t pitch_bytes,
+                     float *out);
+
+/* Same with device-resident input/output (no copies); out_pitch in floats.  Asynchronous on the context
+ * stream unless `sync` is non-zero. */
+int dctc_energy_full_dev(dctc_context *ctx, const uint8_t *d_img, int w, int h, int channels,
+                         size_t pitch_bytes, float *d_out, size_t out_pitch, int sync);
+
+/* Batch of n_frames equally sized frames (BASELINE config 4), one launch. */
+int dctc_energy_batch_dev(dctc_context *ctx, const uint8_t *d_imgs, int n_frames, size_t frame_stride_bytes,
+                          int w, int h, int channels, size_t pitch_bytes, float *d_out,
+                          size_t out_frame_stride, size_t out_pitch, int sync);
+
+/* Row band of a taller image (BASELINE config 5).  d_band holds `band_rows` rows; d_top points to the
+ * top_rows image rows directly above the band (in image order, so its last row touches the band) and d_bot to
+ * the bot_rows rows directly below.  Either may be NULL with 0 rows at the image edge, where
+ * the reference's edge replication (src/render.c:122-132) applies.  d_top / d_bot may point into a peer
+ * GPU's memory (NVLink P2P): the kernel then reads the halo straight from the neighbour, no exchange step.
+ * Needs blocksize/2-1 rows above and blocksize/2 rows below for an exact result. */
+int dctc_energy_band_dev(dctc_context *ctx, const uint8_t *d_band, int w, int band_rows, int channels,
+                         size_t pitch_bytes, const uint8_t *d_top, int top_rows, size_t top_pitch_bytes,
+                         const uint8_t *d_bot, int bot_rows, size_t bot_pitch_bytes, float *d_out,
+                         size_t out_pitch, int sync);
+
+/* Host-buffer batch through pinned staging with copy/compute overlap (what bench.py's e2e measures). */
+int dctc_energy_batch(dctc_context *ctx, const uint8_t *imgs, int n_frames, size_t frame_stride_bytes, int w,
+                      int h, int channels, size_t pitch_bytes, float *out, size_t out_frame_stride);
+
+/* ---- K2: carver session, incremental per-seam energy ---------------------------------------------------
+ * Replaces liblqr's update_emap, which re-invokes the callback for the pixels within +-radius of the removed
+ * seam (radius = blocksize/2 as registered at src/render.c:314-315). */
+
+/* Uploads the image, keeps it device-resident and builds the full map (K1). */
+int dctc_carver_load(dctc_context *ctx, const uint8_t *img, int w, int h, int channels, size_t pitch_bytes);
+/* Current carver width / height. */
+int dctc_carver_width(const dctc_context *ctx);
+int dctc_carver_height(const dctc_context *ctx);
+/* Copies the current w*h energy map to the host (row pitch = current width). */
+int dctc_carver_energy(dctc_context *ctx, float *out);
+/* Removes one vertical seam (seam_x[y] = column removed in row y, h entries), compacts the device image and
+ * energy planes and recomputes the energy only in the band the seam touched:
+ *   row y: x in [min_{|y'-y|<=r} seam_x[y'] - r, max_{|y'-y|<=r} seam_x[y'] + r - 1] clipped to [0, w-2].
+ * On return *xmin / *xmax (h entries each, may be NULL) hold that band and band_out (may be NULL) receives, row
+ * by row, the xmax[y]-xmin[y]+1 recomputed values packed back to back. */
+int dctc_carve_and_update(dctc_context *ctx, const int *seam_x, float *band_out, int *xmin, int *xmax);
+/* Copies the current (carved) interleaved image back to the host, pitch = w*channels. */
+int dctc_carver_image(dctc_context *ctx, uint8_t *out);
+/* Whole retarget loop on the device (energy -> seam DP -> back-track -> carve -> band update), `n_seams`
+ * vertical seams; seams_out (may be NULL) receives n_seams*h removed columns in the coordinates of the image
+ * at the time of removal.  Mirrors lqr_carver_resize(carver, w - n_seams, h) (src/render.c:377) with
+ * delta_x = 1, rigidity = 0 (src/render.c:313). */
+int dctc_carver_resize_width(dctc_context *ctx, int n_seams, int *seams_out);
+
+/* ---- per-pixel symbol, kept for ABI parity ---------------------------------------------------------------
+ * Same signature as the reference's LqrEnergyFunc dct_pixel_energy (src/render.c:134).  `extra_data` must
+ * point to a DctcCarverEnergyParams.  A per-pixel call cannot be GPU-backed, so it is served from the host
+ * mirror of the device energy map of the context's carver session (valid when (w,h) match the session's
+ * current size); otherwise it returns NaN and records DCTC_ERR_STATE.  `rw` is not dereferenced. */
+struct DctcLqrReadingWindow_;
+float dctc_pixel_energy(int x, int y, int w, int h, struct DctcLqrReadingWindow_ *rw, void *extra_data);
+
+/* ---- synthetic inputs (bench / tests) ----------------------------------------------------------------- */
+
+/* Counter-based generator, identical on CPU (tests) and GPU: byte = hash32(seed, frame, y, x, c) >> 24 for
+ * pattern 0 (noise); patterns 1..3 are the gradient / checkerboard / step-edge stress images of SURVEY §8d. */
+int dctc_synth_fill_dev(dctc_context *ctx, uint8_t *d_img, int n_frames, size_t frame_stride_bytes, int w, int h,
+                        int channels, size_t pitch_bytes, uint32_t seed, int pattern, int first_frame, int y_offset);
+uint8_t dctc_synth_byte(uint32_t seed, uint32_t frame, uint32_t y, uint32_t x, uint32_t c, int pattern);
+
+/* ---- raw device memory helpers so that C / ctypes callers need no other CUDA binding -------------------- */
+int dctc_dev_alloc(dctc_context *ctx, void **d_ptr, size_t bytes);
+int dctc_dev_free(dctc_context *ctx, void *d_ptr);
+int dctc_host_alloc_pinned(void **h_ptr, size_t bytes);
+int dctc_host_free_pinned(void *h_ptr);
+int dctc_memcpy_h2d(dctc_context *ctx, void *d_dst, const void *h_src, size_t bytes);
+int dctc_memcpy_d2h(dctc_context *ctx, void *h_dst, const void *d_src, size_t bytes);
+int dctc_memset_dev(dctc_context *ctx, void *d_ptr, int value, size_t bytes);
+int dctc_sync(dctc_context *ctx);
+/* Event timing on the context stream: returns elapsed milliseconds between begin and end. */
+int dctc_timer_begin(dctc_context *ctx);
+int dctc_timer_end(dctc_context *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCTC_H */
