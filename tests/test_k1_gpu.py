@@ -1,0 +1,201 @@
+"""GPU parity tests of K1 (full energy map), through the C ABI, against the oracle / compiled reference / golden
+vectors.  Tolerance (FP32 CUDA path vs the double-precision reference): |err| <= 1e-6 + 4e-6*|ref|."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import dct_carver_b200 as dc
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "energy_golden.npz"))
+N_GOLD = sum(1 for k in GOLD.files if k.startswith("img_"))
+KERNELS = [dc.KERNEL_FP32_TILE]
+
+
+def check_with_flips(got, img, b, e, t, max_flip_frac=2e-3):
+    """Non-uniform weights: a near-tie between an edge atom and a texture atom may resolve differently in FP32
+    (SURVEY section 7 'class flips').  Such pixels must equal the other class's product and be rare."""
+    want, cls = ol.oracle_energy(img, b, e, t, want_class=True)
+    got64, want64 = got.astype(np.float64), want.astype(np.float64)
+    ok = np.abs(got64 - want64) <= ol.ABS_TOL + ol.REL_TOL * np.abs(want64)
+    if e == t or ok.all():
+        assert ok.all(), ol.parity(got, want)
+        return 0
+    w_this = np.where(cls == 1, e, t).astype(np.float64)
+    w_other = np.where(cls == 1, t, e).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        alt = np.where(w_this > 0, want64 / w_this * w_other, np.nan)
+    flip_ok = np.abs(got64 - alt) <= ol.ABS_TOL + 1e-5 * np.abs(alt)
+    assert (ok | flip_ok).all(), "mismatch that is not a class flip: %d" % (~(ok | flip_ok)).sum()
+    flips = int((~ok).sum())
+    assert flips <= max(2, max_flip_frac * got.size), flips
+    return flips
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = dc.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("i", range(N_GOLD))
+def test_golden_vectors(ctx, i, kernel):
+    img = GOLD["img_%02d" % i]
+    want = GOLD["en_%02d" % i]
+    b = int(GOLD["meta_%02d" % i][0])
+    e, t = (float(v) for v in GOLD["wts_%02d" % i])
+    ctx.set_params(b, e, t)
+    ctx.set_kernel(kernel if b == 8 else dc.KERNEL_AUTO)
+    got = ctx.energy_full(img)
+    if e == t:
+        ol.assert_parity(got, want)
+    else:
+        check_with_flips(got, img, b, e, t)
+
+
+@pytest.mark.parametrize("b", [2, 4, 8, 16])
+@pytest.mark.parametrize("wts", [(0.5, 0.5), (0.8, 0.2), (1.0, 0.0)])
+@pytest.mark.parametrize("case", [(0, 3, 200, 150), (0, 1, 131, 67), (3, 3, 96, 130), (1, 4, 70, 41), (2, 2, 65, 33),
+                                  (0, 3, 1, 1), (0, 1, 3, 2), (0, 3, 7, 40), (0, 1, 64, 32), (0, 3, 65, 33)])
+def test_parity_vs_oracle(ctx, b, wts, case):
+    pattern, ch, w, h = case
+    img = ol.synth_image(w, h, ch, 1000 + b, pattern)
+    ctx.set_params(b, *wts)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    got = ctx.energy_full(img)
+    assert got.shape == (h, w)
+    check_with_flips(got, img, b, *wts)
+
+
+@pytest.mark.parametrize("b", [2, 4, 8, 16])
+def test_512_grey_config1_against_best_checker(ctx, b):
+    """BASELINE config 1: 512x512 8-bit grey, full map; checker = the compiled reference when it travelled."""
+    img = ol.synth_image(512, 512, 1, 0xD0C7CA12, 0)
+    ctx.set_params(b, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    got = ctx.energy_full(img)
+    ol.assert_parity(got, ol.best_energy(img, b, 0.5, 0.5))
+
+
+def test_pitch_and_subimage(ctx):
+    """Row pitch larger than w*channels (the carver hands us sub-rectangles of bigger buffers)."""
+    big = ol.synth_image(160, 90, 3, 5, 0)
+    sub = np.ascontiguousarray(big[10:70, 20:140])
+    ctx.set_params(8, 0.5, 0.5)
+    want = ctx.energy_full(sub)
+    out = np.empty((60, 120), np.float32)
+    view = big[10:70, 20:140]
+    rc = dc.lib().dctc_energy_full(ctx.handle, C.c_void_p(view.ctypes.data), 120, 60, 3, big.strides[0],
+                                   C.c_void_p(out.ctypes.data))
+    assert rc == 0
+    assert np.array_equal(out, want)
+
+
+def test_error_behaviour(ctx):
+    L = dc.lib()
+    p = dc.EnergyParameters(edges=0.5, textures=0.5, blocksize=3)
+    assert L.dctc_set_params(ctx.handle, C.byref(p)) == dc.ERR_BLOCKSIZE     # dct.c:89-92 -> error()
+    img = np.zeros((4, 4, 3), np.uint8)
+    out = np.zeros((4, 4), np.float32)
+    assert L.dctc_energy_full(ctx.handle, img.ctypes.data, 4, 4, 5, 20, out.ctypes.data) == dc.ERR_INVALID
+    assert L.dctc_energy_full(ctx.handle, img.ctypes.data, 4, 4, 3, 8, out.ctypes.data) == dc.ERR_INVALID
+    assert L.dctc_energy_full(ctx.handle, img.ctypes.data, 0, 4, 3, 12, out.ctypes.data) == dc.ERR_INVALID
+    assert L.dctc_energy_full(ctx.handle, None, 4, 4, 3, 12, out.ctypes.data) == dc.ERR_INVALID
+    ctx.set_params(8, 0.5, 0.5)
+
+
+def test_batch_equals_single_frames(ctx):
+    n, h, w, ch = 5, 45, 77, 3
+    imgs = np.stack([ol.synth_image(w, h, ch, 42, 0, frame=f) for f in range(n)])
+    ctx.set_params(8, 0.5, 0.5)
+    got = ctx.energy_batch(imgs)
+    for f in range(n):
+        assert np.array_equal(got[f], ctx.energy_full(imgs[f]))
+
+
+def test_device_synth_matches_host_generator(ctx):
+    w, h, ch, n = 130, 37, 3, 3
+    d = ctx.dev_alloc(n * w * h * ch)
+    for pattern in range(4):
+        ctx.synth_fill_dev(d, n, w * h * ch, w, h, ch, w * ch, 99, pattern, first_frame=2, y_offset=11)
+        out = np.empty((n, h, w, ch), np.uint8)
+        ctx.d2h(out, d)
+        for f in range(n):
+            assert np.array_equal(out[f], ol.synth_image(w, h, ch, 99, pattern, frame=2 + f, y_offset=11)), pattern
+    ctx.dev_free(d)
+
+
+def _band_run(ctx, img, bounds, b):
+    """Energy of a tall image computed band by band with device-resident halos (config 5 on one GPU)."""
+    h, w, ch = img.shape
+    pitch = w * ch
+    d_img = ctx.dev_alloc(img.nbytes)
+    d_out = ctx.dev_alloc(h * w * 4)
+    ctx.h2d(d_img, img)
+    r_top, r_bot = b // 2 - 1, b // 2
+    for (y0, y1) in bounds:
+        t = min(r_top, y0)
+        bt = min(r_bot, h - y1)
+        ctx.energy_band_dev(d_img + y0 * pitch, w, y1 - y0, ch, pitch,
+                            d_img + (y0 - t) * pitch if t else None, t, pitch,
+                            d_img + y1 * pitch if bt else None, bt, pitch,
+                            d_out + y0 * w * 4, w)
+    out = np.empty((h, w), np.float32)
+    ctx.d2h(out, d_out)
+    ctx.dev_free(d_img)
+    ctx.dev_free(d_out)
+    return out
+
+
+@pytest.mark.parametrize("b", [2, 4, 8, 16])
+def test_row_bands_with_halo_equal_full_image(ctx, b):
+    img = ol.synth_image(150, 101, 3, 7, 0)
+    ctx.set_params(b, 0.5, 0.5)
+    full = ctx.energy_full(img)
+    got = _band_run(ctx, img, [(0, 13), (13, 50), (50, 51), (51, 101)], b)
+    assert np.array_equal(got, full)
+
+
+def test_full_size_4k_properties(ctx):
+    """BASELINE config 2 (3840x2160 RGB) through size-independent properties: (1) random crops re-evaluated by the
+    oracle on crop+halo agree in the crop interior (the operator is local); (2) row-band decomposition is bit-equal;
+    (3) the checksum of per-row checksums is reproducible across two runs."""
+    w, h, ch = 3840, 2160, 3
+    ctx.set_params(8, 0.5, 0.5)
+    d_img = ctx.dev_alloc(w * h * ch)
+    ctx.synth_fill_dev(d_img, 1, 0, w, h, ch, w * ch, 0xD0C7CA13, 0)
+    img = np.empty((h, w, ch), np.uint8)
+    ctx.d2h(img, d_img)
+    assert np.array_equal(img[1000:1003, 2000:2005], ol.synth_image(w, h, ch, 0xD0C7CA13, 0)[1000:1003, 2000:2005])
+    d_out = ctx.dev_alloc(w * h * 4)
+    ctx.energy_batch_dev(d_img, 1, 0, w, h, ch, w * ch, d_out, 0, w, sync=True)
+    en = np.empty((h, w), np.float32)
+    ctx.d2h(en, d_out)
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        y0 = int(rng.integers(8, h - 56))
+        x0 = int(rng.integers(8, w - 56))
+        crop = img[y0 - 8:y0 + 56, x0 - 8:x0 + 56]
+        want = ol.best_energy(crop, 8, 0.5, 0.5)[8:-8, 8:-8]
+        ol.assert_parity(en[y0:y0 + 48, x0:x0 + 48], want)
+    # corners: the edge replication at full size (window offsets -3..+4, so a 48-px crop covers 40 px exactly)
+    tl = ol.best_energy(np.ascontiguousarray(img[:48, :48]), 8, 0.5, 0.5)[:40, :40]
+    ol.assert_parity(en[:40, :40], tl)
+    br = ol.best_energy(np.ascontiguousarray(img[h - 48:, w - 48:]), 8, 0.5, 0.5)[8:, 8:]
+    ol.assert_parity(en[h - 40:, w - 40:], br)
+    tr = ol.best_energy(np.ascontiguousarray(img[:48, w - 48:]), 8, 0.5, 0.5)[:40, 8:]
+    ol.assert_parity(en[:40, w - 40:], tr)
+    got = _band_run(ctx, img, [(0, 270), (270, 1080), (1080, 1081), (1081, 2160)], 8)
+    assert np.array_equal(got, en)
+    ctx.energy_batch_dev(d_img, 1, 0, w, h, ch, w * ch, d_out, 0, w, sync=True)
+    en2 = np.empty((h, w), np.float32)
+    ctx.d2h(en2, d_out)
+    assert np.float64(en2.sum(axis=1, dtype=np.float64)).sum() == np.float64(en.sum(axis=1, dtype=np.float64)).sum()
+    ctx.dev_free(d_img)
+    ctx.dev_free(d_out)

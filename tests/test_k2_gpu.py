@@ -1,0 +1,92 @@
+"""GPU tests of K2 (carver session: seam removal + incremental band energy) through the C ABI."""
+import numpy as np
+import pytest
+
+import dct_carver_b200 as dc
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = dc.Context(0)
+    yield c
+    c.close()
+
+
+def random_seam(rng, w, h):
+    x = int(rng.integers(0, w))
+    s = np.empty(h, np.int32)
+    for y in range(h):
+        x = int(np.clip(x + rng.integers(-1, 2), 0, w - 1))
+        s[y] = x
+    return s
+
+
+def carve_host(img, seam):
+    h, w, ch = img.shape
+    out = np.empty((h, w - 1, ch), img.dtype)
+    for y in range(h):
+        out[y] = np.delete(img[y], seam[y], axis=0)
+    return out
+
+
+@pytest.mark.parametrize("b", [2, 4, 8, 16])
+@pytest.mark.parametrize("ch", [1, 3])
+def test_incremental_equals_full_recompute(ctx, b, ch):
+    """After every seam the device energy plane must be BIT-identical to K1 run from scratch on the carved image,
+    and within tolerance of the oracle; the reported band must be liblqr's update_emap range."""
+    rng = np.random.default_rng(b * 10 + ch)
+    w, h = 97, 75
+    img = ol.synth_image(w, h, ch, 11, 0)
+    ctx.set_params(b, 0.5, 0.5)
+    ctx.carver_load(img)
+    assert np.array_equal(ctx.carver_energy(), ctx.energy_full(img))
+    r = b // 2
+    cur = img
+    for k in range(12):
+        seam = random_seam(rng, cur.shape[1], h) if k % 4 else np.full(h, (0 if k == 0 else cur.shape[1] - 1), np.int32)
+        band, xmin, xmax = ctx.carve_and_update(seam)
+        cur = carve_host(cur, seam)
+        assert ctx.carver_size() == (cur.shape[1], h)
+        assert np.array_equal(ctx.carver_image(), cur)
+        en = ctx.carver_energy()
+        full = ctx.energy_full(cur)
+        assert np.array_equal(en, full), "seam %d" % k
+        # band limits = SURVEY section 8b formula
+        for y in range(h):
+            lo = min(seam[max(0, y - r):y + r + 1]) - r
+            hi = max(seam[max(0, y - r):y + r + 1]) + r - 1
+            assert xmin[y] == max(lo, 0) and xmax[y] == min(hi, cur.shape[1] - 1)
+        packed = np.concatenate([en[y, xmin[y]:xmax[y] + 1] for y in range(h)])
+        assert np.array_equal(band, packed)
+    ol.assert_parity(ctx.carver_energy(), ol.best_energy(cur, b, 0.5, 0.5))
+
+
+def test_carver_state_errors(ctx):
+    L = dc.lib()
+    c2 = dc.Context(0)
+    seam = np.zeros(4, np.int32)
+    assert L.dctc_carve_and_update(c2.handle, seam.ctypes.data, None, None, None) == dc.ERR_STATE
+    c2.carver_load(np.zeros((4, 6, 3), np.uint8))
+    bad = np.array([0, 1, 6, 2], np.int32)
+    assert L.dctc_carve_and_update(c2.handle, bad.ctypes.data, None, None, None) == dc.ERR_STATE
+    c2.close()
+
+
+def test_per_pixel_symbol_serves_host_mirror(ctx):
+    import ctypes as C
+    img = ol.synth_image(40, 30, 3, 3, 0)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.carver_load(img)
+    en = ctx.carver_energy()
+    p = dc.CarverEnergyParams()
+    p.base.edges, p.base.textures, p.base.blocksize = 0.5, 0.5, 8
+    p.gpu = ctx.handle.value
+    L = dc.lib()
+    assert L.dctc_pixel_energy(7, 9, 40, 30, None, C.byref(p)) == en[9, 7]
+    assert np.isnan(L.dctc_pixel_energy(7, 9, 41, 30, None, C.byref(p)))   # stale size: loud, not silently wrong
+    ctx.carve_and_update(np.full(30, 5, np.int32), want_band=False)
+    en2 = ctx.carver_energy()
+    assert L.dctc_pixel_energy(7, 9, 39, 30, None, C.byref(p)) == en2[9, 7]
