@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "dctc_energy_full", "dctc_energy_full_dev", "dctc_energy_batch_dev", "dctc_energy_band_dev", "dctc_energy_batch",
     "dctc_carver_load", "dctc_carver_width", "dctc_carver_height", "dctc_carver_energy", "dctc_carve_and_update",
     "dctc_carver_image", "dctc_carver_resize_width", "dctc_pixel_energy",
-    "dctc_synth_fill_dev", "dctc_synth_byte",
+    "dctc_synth_fill_dev", "dctc_synth_byte", "dctc_ipc_export", "dctc_ipc_open", "dctc_ipc_close",
     "dctc_dev_alloc", "dctc_dev_free", "dctc_host_alloc_pinned", "dctc_host_free_pinned", "dctc_memcpy_h2d",
     "dctc_memcpy_d2h", "dctc_memset_dev", "dctc_sync", "dctc_timer_begin", "dctc_timer_end",
 ]
@@ -90,6 +90,9 @@ def lib():
         "dctc_pixel_energy": (f32, [i32, i32, i32, i32, vp, vp]),
         "dctc_synth_fill_dev": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, u32, i32, i32, i32]),
         "dctc_synth_byte": (C.c_uint8, [u32, u32, u32, u32, u32, i32]),
+        "dctc_ipc_export": (i32, [vp, vp, vp]),
+        "dctc_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
+        "dctc_ipc_close": (i32, [vp, vp]),
         "dctc_dev_alloc": (i32, [vp, C.POINTER(vp), sz]),
         "dctc_dev_free": (i32, [vp, vp]),
         "dctc_host_alloc_pinned": (i32, [C.POINTER(vp), sz]),
@@ -213,6 +216,20 @@ class Context:
 
     def sync(self):
         _check(lib().dctc_sync(self._h), "dctc_sync")
+
+    def ipc_export(self, d_ptr):
+        buf = (C.c_ubyte * 64)()
+        _check(lib().dctc_ipc_export(self._h, C.c_void_p(d_ptr), buf), "dctc_ipc_export")
+        return bytes(buf)
+
+    def ipc_open(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _check(lib().dctc_ipc_open(self._h, buf, C.byref(p)), "dctc_ipc_open")
+        return p.value
+
+    def ipc_close(self, d_ptr):
+        _check(lib().dctc_ipc_close(self._h, C.c_void_p(d_ptr)), "dctc_ipc_close")
 
     def timer_begin(self):
         _check(lib().dctc_timer_begin(self._h), "dctc_timer_begin")

@@ -313,6 +313,36 @@ int dctc_synth_fill_dev(dctc_context* ctx, uint8_t* d_img, int n_frames, size_t 
     return DCTC_OK;
 }
 
+int dctc_ipc_export(dctc_context* ctx, void* d_ptr, unsigned char handle[DCTC_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == DCTC_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!ctx || !d_ptr || !handle) return DCTC_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t hnd;
+    CK(ctx, cudaIpcGetMemHandle(&hnd, d_ptr));
+    memcpy(handle, &hnd, sizeof(hnd));
+    return DCTC_OK;
+}
+
+int dctc_ipc_open(dctc_context* ctx, const unsigned char handle[DCTC_IPC_HANDLE_BYTES], void** d_peer_ptr)
+{
+    if (!ctx || !handle || !d_peer_ptr) return DCTC_ERR_INVALID;
+    *d_peer_ptr = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle, sizeof(hnd));
+    CK(ctx, cudaIpcOpenMemHandle(d_peer_ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return DCTC_OK;
+}
+
+int dctc_ipc_close(dctc_context* ctx, void* d_peer_ptr)
+{
+    if (!ctx || !d_peer_ptr) return DCTC_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaIpcCloseMemHandle(d_peer_ptr));
+    return DCTC_OK;
+}
+
 int dctc_dev_alloc(dctc_context* ctx, void** d_ptr, size_t bytes)
 {
     if (!ctx || !d_ptr) return DCTC_ERR_INVALID;

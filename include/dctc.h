@@ -159,6 +159,15 @@ int dctc_synth_fill_dev(dctc_context *ctx, uint8_t *d_img, int n_frames, size_t 
                         int channels, size_t pitch_bytes, uint32_t seed, int pattern, int first_frame, int y_offset);
 uint8_t dctc_synth_byte(uint32_t seed, uint32_t frame, uint32_t y, uint32_t x, uint32_t c, int pattern);
 
+/* ---- peer access for row-band sharding, one process per GPU (BASELINE config 5) ---------------------------
+ * A rank exports its band buffer with dctc_ipc_export (64-byte CUDA IPC handle), sends the handle to its
+ * neighbours over any channel, and they map it with dctc_ipc_open.  The mapped pointer is then passed as
+ * d_top / d_bot of dctc_energy_band_dev, so the halo rows are loaded over NVLink by the energy kernel itself. */
+#define DCTC_IPC_HANDLE_BYTES 64
+int dctc_ipc_export(dctc_context *ctx, void *d_ptr, unsigned char handle[DCTC_IPC_HANDLE_BYTES]);
+int dctc_ipc_open(dctc_context *ctx, const unsigned char handle[DCTC_IPC_HANDLE_BYTES], void **d_peer_ptr);
+int dctc_ipc_close(dctc_context *ctx, void *d_peer_ptr);
+
 /* ---- raw device memory helpers so that C / ctypes callers need no other CUDA binding -------------------- */
 int dctc_dev_alloc(dctc_context *ctx, void **d_ptr, size_t bytes);
 int dctc_dev_free(dctc_context *ctx, void *d_ptr);
