@@ -1,0 +1,500 @@
+/* dctc_lqr.c — host-side carver (liblqr subset) + render.c-like glue.  See dctc_lqr.h for what is restated
+ * and from where.  Plain C; the only compute it delegates is the energy (GPU batch hooks or a callback). */
+#include "dctc_lqr.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+struct DctcLqrCarver_ {
+    uint8_t *rgb;          /* current image, row pitch = w*ch (compacted after every seam) */
+    int w, h, ch;
+    int w_start, h_start;  /* size handed to lqr_carver_new */
+    int transposed;
+    int delta_x;
+    float rigidity;
+    DctcLqrEnergyFunc nrg;
+    int radius, reader;
+    void *extra;
+    dctc_context *gpu;
+    int dump_vmaps;
+    int *vs;               /* visibility over the start frame of the first carve op */
+    int vs_w, vs_h, vs_depth;
+    int *seams;            /* all seams, concatenated */
+    int n_seams, seam_len, seams_cap;
+    uint8_t *line;         /* scan_line buffer */
+    int scan_pos;
+    double timing[3];
+};
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
+double dctc_lqr_rwindow_read(DctcLqrReadingWindow *rw, int dx, int dy, int channel)
+{
+    int xx = rw->x + dx, yy = rw->y + dy;
+    (void) channel;
+    if (dx < -rw->radius || dx > rw->radius || dy < -rw->radius || dy > rw->radius) return 0.0;
+    if (xx < 0 || xx >= rw->w || yy < 0 || yy >= rw->h) return 0.0;
+    return rw->luma[(size_t) yy * rw->w + xx];
+}
+
+int dctc_lqr_rwindow_get_radius(DctcLqrReadingWindow *rw) { return rw->radius; }
+
+DctcLqrCarver *dctc_lqr_carver_new(uint8_t *buffer, int width, int height, int channels)
+{
+    DctcLqrCarver *r;
+    if (!buffer || width <= 0 || height <= 0 || channels < 1 || channels > 4) return NULL;
+    r = (DctcLqrCarver *) calloc(1, sizeof(*r));
+    if (!r) return NULL;
+    r->rgb = buffer;
+    r->w = r->w_start = width;
+    r->h = r->h_start = height;
+    r->ch = channels;
+    r->delta_x = 1;
+    r->reader = DCTC_LQR_ER_LUMA;
+    return r;
+}
+
+int dctc_lqr_carver_init(DctcLqrCarver *r, int delta_x, float rigidity)
+{
+    if (!r || delta_x < 0) return DCTC_LQR_ERROR;
+    r->delta_x = delta_x;
+    r->rigidity = rigidity;
+    return DCTC_LQR_OK;
+}
+
+int dctc_lqr_carver_set_energy_function(DctcLqrCarver *r, DctcLqrEnergyFunc f, int radius, int reader_type, void *extra)
+{
+    if (!r || radius < 0) return DCTC_LQR_ERROR;
+    r->nrg = f;
+    r->radius = radius;
+    r->reader = reader_type;
+    r->extra = extra;
+    return DCTC_LQR_OK;
+}
+
+int dctc_lqr_carver_attach_gpu(DctcLqrCarver *r, dctc_context *gpu)
+{
+    if (!r) return DCTC_LQR_ERROR;
+    r->gpu = gpu;
+    return DCTC_LQR_OK;
+}
+
+void dctc_lqr_carver_set_dump_vmaps(DctcLqrCarver *r) { if (r) r->dump_vmaps = 1; }
+int dctc_lqr_carver_get_width(const DctcLqrCarver *r) { return r->transposed ? r->h : r->w; }
+int dctc_lqr_carver_get_height(const DctcLqrCarver *r) { return r->transposed ? r->w : r->h; }
+int dctc_lqr_carver_get_channels(const DctcLqrCarver *r) { return r->ch; }
+int dctc_lqr_carver_scan_by_row(const DctcLqrCarver *r) { return !r->transposed; }
+void dctc_lqr_carver_scan_reset(DctcLqrCarver *r) { r->scan_pos = 0; }
+const double *dctc_lqr_carver_timing(const DctcLqrCarver *r) { return r->timing; }
+
+int dctc_lqr_carver_scan_line(DctcLqrCarver *r, int *n, uint8_t **rgb)
+{
+    if (r->scan_pos >= r->h) { r->scan_pos = 0; return 0; }
+    *n = r->scan_pos;
+    *rgb = r->rgb + (size_t) r->scan_pos * r->w * r->ch;
+    r->scan_pos++;
+    return 1;
+}
+
+void dctc_lqr_carver_destroy(DctcLqrCarver *r)
+{
+    if (!r) return;
+    free(r->rgb); free(r->vs); free(r->seams); free(r->line);
+    free(r);
+}
+
+const int *dctc_lqr_carver_vmap(const DctcLqrCarver *r, int *w0, int *h0, int *depth)
+{
+    if (w0) *w0 = r->vs_w;
+    if (h0) *h0 = r->vs_h;
+    if (depth) *depth = r->vs_depth;
+    return r->vs;
+}
+
+const int *dctc_lqr_carver_seams(const DctcLqrCarver *r, int *n_seams, int *seam_len)
+{
+    if (n_seams) *n_seams = r->n_seams;
+    if (seam_len) *seam_len = r->seam_len;
+    return r->seams;
+}
+
+/* liblqr LQR_ER_LUMA reader [from memory]: channels normalised to [0,1], Rec.709 weights, times alpha */
+static double luma_px(const uint8_t *p, int ch)
+{
+    double v;
+    if (ch >= 3) v = 0.2126 * ((double) p[0] / 255.0) + 0.7152 * ((double) p[1] / 255.0) + 0.0722 * ((double) p[2] / 255.0);
+    else v = (double) p[0] / 255.0;
+    if (ch == 2 || ch == 4) v *= (double) p[ch - 1] / 255.0;
+    return v;
+}
+
+static void fill_luma(const DctcLqrCarver *r, double *luma)
+{
+    int x, y;
+    for (y = 0; y < r->h; y++)
+        for (x = 0; x < r->w; x++) luma[(size_t) y * r->w + x] = luma_px(r->rgb + ((size_t) y * r->w + x) * r->ch, r->ch);
+}
+
+static void band_limits(const int *seam, int y, int h, int w, int rad, int *xmin, int *xmax)
+{
+    int lo = seam[y], hi = seam[y], d;
+    for (d = -rad; d <= rad; d++) {
+        int yy = y + d;
+        if (yy < 0 || yy >= h) continue;
+        if (seam[yy] < lo) lo = seam[yy];
+        if (seam[yy] > hi) hi = seam[yy];
+    }
+    lo -= rad; hi += rad - 1;
+    *xmin = lo < 0 ? 0 : lo;
+    *xmax = hi > w - 1 ? w - 1 : hi;
+}
+
+/* m[y][x] = en[y][x] + min over parents x-dx..x+dx (clipped), first strict minimum scanning left to right */
+static float min_parent(const float *mrow_prev, int x, int w, int dx)
+{
+    int x1, lo = x - dx < 0 ? 0 : x - dx, hi = x + dx > w - 1 ? w - 1 : x + dx;
+    float best = mrow_prev[lo];
+    for (x1 = lo + 1; x1 <= hi; x1++)
+        if (mrow_prev[x1] < best) best = mrow_prev[x1];
+    return best;
+}
+
+static int argmin_parent(const float *mrow_prev, int x, int w, int dx)
+{
+    int x1, lo = x - dx < 0 ? 0 : x - dx, hi = x + dx > w - 1 ? w - 1 : x + dx, arg = lo;
+    float best = mrow_prev[lo];
+    for (x1 = lo + 1; x1 <= hi; x1++)
+        if (mrow_prev[x1] < best) { best = mrow_prev[x1]; arg = x1; }
+    return arg;
+}
+
+/* removes k vertical seams from the current frame */
+static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
+{
+    const int P = r->w, h = r->h, ch = r->ch, dx = r->delta_x;
+    float *en = NULL, *m = NULL, *band = NULL;
+    int *raw = NULL, *seam = NULL, *xmin = NULL, *xmax = NULL;
+    double *luma = NULL;
+    DctcLqrReadingWindow rw;
+    int x, y, s, rc = DCTC_LQR_NOMEM;
+    double t0;
+
+    if (k <= 0) return DCTC_LQR_OK;
+    if (k >= r->w) return DCTC_LQR_ERROR;
+    if (!r->gpu && !r->nrg) return DCTC_LQR_ERROR;
+    en = (float *) malloc(sizeof(float) * (size_t) P * h);
+    m = (float *) malloc(sizeof(float) * (size_t) P * h);
+    raw = (int *) malloc(sizeof(int) * (size_t) P * h);
+    seam = (int *) malloc(sizeof(int) * h);
+    xmin = (int *) malloc(sizeof(int) * h);
+    xmax = (int *) malloc(sizeof(int) * h);
+    band = (float *) malloc(sizeof(float) * (size_t) h * (4 * (r->radius > 0 ? r->radius : 1) + 2));
+    if (!r->gpu) luma = (double *) malloc(sizeof(double) * (size_t) P * h);
+    if (!en || !m || !raw || !seam || !xmin || !xmax || !band || (!r->gpu && !luma)) goto done;
+    if (r->n_seams + k > r->seams_cap || r->seam_len != h) {
+        int *ns;
+        if (r->seam_len != h) { r->n_seams = 0; r->seam_len = h; }
+        ns = (int *) realloc(r->seams, sizeof(int) * (size_t) (r->n_seams + k) * h);
+        if (!ns) goto done;
+        r->seams = ns; r->seams_cap = r->n_seams + k;
+    }
+    if (record_vs) {
+        free(r->vs);
+        r->vs = (int *) calloc((size_t) P * h, sizeof(int));
+        if (!r->vs) goto done;
+        r->vs_w = P; r->vs_h = h; r->vs_depth = 0;
+    }
+    for (y = 0; y < h; y++)
+        for (x = 0; x < P; x++) raw[(size_t) y * P + x] = x;
+
+    /* build_emap (en rows are kept compact: pitch = current width) */
+    t0 = now_s();
+    rc = DCTC_LQR_ERROR;
+    if (r->gpu) {
+        if (dctc_carver_load(r->gpu, r->rgb, r->w, h, ch, (size_t) r->w * ch) != DCTC_OK) goto done;
+        if (dctc_carver_energy(r->gpu, en) != DCTC_OK) goto done;
+    } else {
+        fill_luma(r, luma);
+        rw.luma = luma; rw.w = r->w; rw.h = h; rw.radius = r->radius;
+        for (y = 0; y < h; y++)
+            for (x = 0; x < r->w; x++) {
+                rw.x = x; rw.y = y;
+                en[(size_t) y * r->w + x] = r->nrg(x, y, r->w, h, &rw, r->extra);
+            }
+    }
+    r->timing[0] += now_s() - t0;
+
+    /* build_mmap */
+    t0 = now_s();
+    memcpy(m, en, sizeof(float) * r->w);
+    for (y = 1; y < h; y++)
+        for (x = 0; x < r->w; x++)
+            m[(size_t) y * r->w + x] = en[(size_t) y * r->w + x] + min_parent(m + (size_t) (y - 1) * r->w, x, r->w, dx);
+    r->timing[1] += now_s() - t0;
+
+    for (s = 0; s < k; s++) {
+        const int w = r->w, w1 = w - 1;
+        int clo = 0, chi = -1; /* changed interval of the previous row in update_mmap */
+        /* build_vpath: leftmost minimum of the last row, then back-track */
+        t0 = now_s();
+        {
+            const float *last = m + (size_t) (h - 1) * w;
+            int best = 0;
+            for (x = 1; x < w; x++)
+                if (last[x] < last[best]) best = x;
+            seam[h - 1] = best;
+            for (y = h - 1; y > 0; y--) seam[y - 1] = argmin_parent(m + (size_t) (y - 1) * w, seam[y], w, dx);
+        }
+        memcpy(r->seams + (size_t) r->n_seams * h, seam, sizeof(int) * h);
+        r->n_seams++;
+        /* update_vsmap + carve: compact rgb, raw, en, m from pitch w to pitch w-1 */
+        for (y = 0; y < h; y++) {
+            const int sx = seam[y];
+            if (record_vs) r->vs[(size_t) y * P + raw[(size_t) y * w + sx]] = r->vs_depth + 1;
+            memmove(r->rgb + (size_t) y * w1 * ch, r->rgb + (size_t) y * w * ch, (size_t) sx * ch);
+            memmove(r->rgb + ((size_t) y * w1 + sx) * ch, r->rgb + ((size_t) y * w + sx + 1) * ch, (size_t) (w1 - sx) * ch);
+            memmove(raw + (size_t) y * w1, raw + (size_t) y * w, sizeof(int) * sx);
+            memmove(raw + (size_t) y * w1 + sx, raw + (size_t) y * w + sx + 1, sizeof(int) * (w1 - sx));
+            memmove(en + (size_t) y * w1, en + (size_t) y * w, sizeof(float) * sx);
+            memmove(en + (size_t) y * w1 + sx, en + (size_t) y * w + sx + 1, sizeof(float) * (w1 - sx));
+            memmove(m + (size_t) y * w1, m + (size_t) y * w, sizeof(float) * sx);
+            memmove(m + (size_t) y * w1 + sx, m + (size_t) y * w + sx + 1, sizeof(float) * (w1 - sx));
+        }
+        if (record_vs) r->vs_depth++;
+        r->w = w1;
+        r->timing[2] += now_s() - t0;
+
+        /* update_emap: only the band the seam touched */
+        t0 = now_s();
+        if (r->gpu) {
+            size_t off = 0;
+            if (dctc_carve_and_update(r->gpu, seam, band, xmin, xmax) != DCTC_OK) { rc = DCTC_LQR_ERROR; goto done; }
+            for (y = 0; y < h; y++) {
+                const int n = xmax[y] - xmin[y] + 1;
+                if (n > 0) { memcpy(en + (size_t) y * w1 + xmin[y], band + off, sizeof(float) * n); off += n; }
+            }
+        } else {
+            fill_luma(r, luma);
+            rw.luma = luma; rw.w = w1; rw.h = h; rw.radius = r->radius;
+            for (y = 0; y < h; y++) {
+                band_limits(seam, y, h, w1, r->radius, &xmin[y], &xmax[y]);
+                for (x = xmin[y]; x <= xmax[y]; x++) {
+                    rw.x = x; rw.y = y;
+                    en[(size_t) y * w1 + x] = r->nrg(x, y, w1, h, &rw, r->extra);
+                }
+            }
+        }
+        r->timing[0] += now_s() - t0;
+
+        /* update_mmap: recompute only where en changed, where the seam disturbed the parent sets, and below
+         * cells whose value actually changed (cone of delta_x per row); identical to a full rebuild */
+        t0 = now_s();
+        for (y = 0; y < h; y++) {
+            float *mrow = m + (size_t) y * w1;
+            const float *erow = en + (size_t) y * w1;
+            int lo = xmin[y], hi = xmax[y], nlo = w1, nhi = -1;
+            if (y > 0) {
+                const int s0 = seam[y - 1] < seam[y] ? seam[y - 1] : seam[y];
+                const int s1 = seam[y - 1] > seam[y] ? seam[y - 1] : seam[y];
+                if (s0 - 2 < lo) lo = s0 - 2;
+                if (s1 + 1 > hi) hi = s1 + 1;
+                if (chi >= clo) {
+                    if (clo - dx < lo) lo = clo - dx;
+                    if (chi + dx > hi) hi = chi + dx;
+                }
+            }
+            if (lo < 0) lo = 0;
+            if (hi > w1 - 1) hi = w1 - 1;
+            for (x = lo; x <= hi; x++) {
+                const float v = y == 0 ? erow[x] : erow[x] + min_parent(mrow - w1, x, w1, dx);
+                if (v != mrow[x]) {
+                    mrow[x] = v;
+                    if (x < nlo) nlo = x;
+                    nhi = x;
+                }
+            }
+            clo = nlo; chi = nhi;
+        }
+        r->timing[1] += now_s() - t0;
+    }
+    rc = DCTC_LQR_OK;
+done:
+    free(en); free(m); free(raw); free(seam); free(xmin); free(xmax); free(band); free(luma);
+    return rc;
+}
+
+static int transpose(DctcLqrCarver *r)
+{
+    const int w = r->w, h = r->h, ch = r->ch;
+    int x, y;
+    uint8_t *t = (uint8_t *) malloc((size_t) w * h * ch);
+    if (!t) return DCTC_LQR_NOMEM;
+    for (y = 0; y < h; y++)
+        for (x = 0; x < w; x++) memcpy(t + ((size_t) x * h + y) * ch, r->rgb + ((size_t) y * w + x) * ch, ch);
+    free(r->rgb);
+    r->rgb = t; r->w = h; r->h = w;
+    r->transposed = !r->transposed;
+    return DCTC_LQR_OK;
+}
+
+/* lqr_carver_resize: width first, then height (through a transposed frame) [liblqr, from memory].
+ * Enlarging (duplicating seams) is outside the energy hot path and not provided. */
+int dctc_lqr_carver_resize(DctcLqrCarver *r, int w1, int h1)
+{
+    int rc, first = r->dump_vmaps;
+    if (!r || w1 <= 0 || h1 <= 0) return DCTC_LQR_ERROR;
+    if (w1 > dctc_lqr_carver_get_width(r) || h1 > dctc_lqr_carver_get_height(r)) return DCTC_LQR_ERROR;
+    if (w1 < r->w) {
+        rc = carve_vertical(r, r->w - w1, first);
+        if (rc) return rc;
+        first = 0;
+    }
+    if (h1 < r->h) {
+        rc = transpose(r);
+        if (rc) return rc;
+        rc = carve_vertical(r, r->w - h1, first);
+        if (rc) { transpose(r); return rc; }
+        rc = transpose(r);
+        if (rc) return rc;
+    }
+    return DCTC_LQR_OK;
+}
+
+int dctc_lqr_carver_get_energy(DctcLqrCarver *r, float *buffer)
+{
+    int x, y;
+    if (!r || !buffer) return DCTC_LQR_ERROR;
+    if (r->gpu) {
+        if (dctc_carver_load(r->gpu, r->rgb, r->w, r->h, r->ch, (size_t) r->w * r->ch) != DCTC_OK) return DCTC_LQR_ERROR;
+        return dctc_carver_energy(r->gpu, buffer) == DCTC_OK ? DCTC_LQR_OK : DCTC_LQR_ERROR;
+    }
+    if (!r->nrg) return DCTC_LQR_ERROR;
+    {
+        DctcLqrReadingWindow rw;
+        double *luma = (double *) malloc(sizeof(double) * (size_t) r->w * r->h);
+        if (!luma) return DCTC_LQR_NOMEM;
+        fill_luma(r, luma);
+        rw.luma = luma; rw.w = r->w; rw.h = r->h; rw.radius = r->radius;
+        for (y = 0; y < r->h; y++)
+            for (x = 0; x < r->w; x++) {
+                rw.x = x; rw.y = y;
+                buffer[(size_t) y * r->w + x] = r->nrg(x, y, r->w, r->h, &rw, r->extra);
+            }
+        free(luma);
+    }
+    return DCTC_LQR_OK;
+}
+
+int dctc_lqr_carver_get_energy_image(DctcLqrCarver *r, uint8_t *buffer)
+{
+    size_t i, n = (size_t) r->w * r->h;
+    float lo, hi, *e = (float *) malloc(sizeof(float) * n);
+    int rc;
+    if (!e) return DCTC_LQR_NOMEM;
+    rc = dctc_lqr_carver_get_energy(r, e);
+    if (rc) { free(e); return rc; }
+    for (i = 0; i < n; i++) e[i] = e[i] / (1.0f + e[i]);
+    lo = hi = e[0];
+    for (i = 1; i < n; i++) { if (e[i] < lo) lo = e[i]; if (e[i] > hi) hi = e[i]; }
+    for (i = 0; i < n; i++) buffer[i] = hi > lo ? (uint8_t) (255.0f * (e[i] - lo) / (hi - lo) + 0.5f) : 0;
+    free(e);
+    return DCTC_LQR_OK;
+}
+
+/* ---- render.c-like glue --------------------------------------------------------------------------------- */
+
+void dctc_render_result_free(DctcRenderResult *res)
+{
+    if (!res) return;
+    free(res->image); free(res->energy_image); free(res->vmap); free(res->seams);
+    memset(res, 0, sizeof(*res));
+}
+
+int dctc_render(const uint8_t *img, int w, int h, int channels, const DctcPlugInVals *vals, dctc_context *gpu,
+                DctcLqrEnergyFunc cb, void *cb_extra, DctcRenderResult *res)
+{
+    DctcCarverEnergyParams ep;       /* superset of EnergyParameters: prefix layout of src/render.h:9-18 */
+    DctcLqrCarver *carver;
+    uint8_t *rgb_buffer, *line;
+    int new_w, new_h, y, n, rc = DCTC_ERR_INVALID;
+    const int *seams;
+    double t0 = now_s();
+    const double *tm;
+
+    if (!img || !vals || !res || w <= 0 || h <= 0) return DCTC_ERR_INVALID;
+    if (!gpu && !cb) return DCTC_ERR_NO_DEVICE;     /* no CPU fallback in the product */
+    memset(res, 0, sizeof(*res));
+
+    /* init_carver_from_vals, src/render.c:296-316 */
+    memset(&ep, 0, sizeof(ep));
+    ep.base.edges = vals->edges;
+    ep.base.textures = vals->textures;
+    ep.base.blocksize = vals->blocksize;
+    ep.gpu = gpu;
+    if (gpu) {
+        rc = dctc_set_params(gpu, &ep.base);
+        if (rc != DCTC_OK) return rc;                /* bad blocksize: src/dct.c:89-92 would call error() */
+    }
+    rgb_buffer = (uint8_t *) malloc((size_t) w * h * channels);
+    if (!rgb_buffer) return DCTC_ERR_NOMEM;
+    memcpy(rgb_buffer, img, (size_t) w * h * channels);
+    carver = dctc_lqr_carver_new(rgb_buffer, w, h, channels);
+    if (!carver) { free(rgb_buffer); return DCTC_ERR_INVALID; }
+    dctc_lqr_carver_init(carver, 1, 0);  /* delta_x, rigidity: src/render.c:313 */
+    if (gpu) {
+        dctc_lqr_carver_set_energy_function(carver, (DctcLqrEnergyFunc) dctc_pixel_energy, vals->blocksize / 2,
+                                            DCTC_LQR_ER_LUMA, (void *) &ep);
+        dctc_lqr_carver_attach_gpu(carver, gpu);
+    } else {
+        dctc_lqr_carver_set_energy_function(carver, cb, vals->blocksize / 2, DCTC_LQR_ER_LUMA, cb_extra);
+    }
+
+    /* render, src/render.c:357-377 */
+    if (vals->vertically) { new_w = w; new_h = h + vals->seams_number; }
+    else { new_w = w + vals->seams_number; new_h = h; }
+    rc = DCTC_ERR_UNSUPPORTED;
+    if (new_w > w || new_h > h || new_w <= 0 || new_h <= 0) goto out;
+    if (vals->output_energy) {
+        res->energy_image = (uint8_t *) malloc((size_t) w * h);
+        if (!res->energy_image || dctc_lqr_carver_get_energy_image(carver, res->energy_image)) { rc = DCTC_ERR_CUDA; goto out; }
+    }
+    if (vals->output_seams && vals->seams_number != 0) dctc_lqr_carver_set_dump_vmaps(carver);
+    if (dctc_lqr_carver_resize(carver, new_w, new_h) != DCTC_LQR_OK) { rc = DCTC_ERR_CUDA; goto out; }
+    if (vals->output_seams && vals->seams_number != 0) {
+        int vw, vh, depth;
+        const int *vs = dctc_lqr_carver_vmap(carver, &vw, &vh, &depth);
+        if (vs) {
+            res->vmap = (int *) malloc(sizeof(int) * (size_t) vw * vh);
+            if (res->vmap) memcpy(res->vmap, vs, sizeof(int) * (size_t) vw * vh);
+            res->vmap_depth = depth;
+        }
+    }
+    /* write_carver_to_layer, src/render.c:244-284 */
+    res->new_w = new_w; res->new_h = new_h; res->channels = channels;
+    res->image = (uint8_t *) malloc((size_t) new_w * new_h * channels);
+    if (!res->image) { rc = DCTC_ERR_NOMEM; goto out; }
+    dctc_lqr_carver_scan_reset(carver);
+    while (dctc_lqr_carver_scan_line(carver, &y, &line))
+        memcpy(res->image + (size_t) y * new_w * channels, line, (size_t) new_w * channels);
+    seams = dctc_lqr_carver_seams(carver, &res->n_seams, &res->seam_len);
+    n = res->n_seams * res->seam_len;
+    if (n > 0) {
+        res->seams = (int *) malloc(sizeof(int) * (size_t) n);
+        if (res->seams) memcpy(res->seams, seams, sizeof(int) * (size_t) n);
+    }
+    tm = dctc_lqr_carver_timing(carver);
+    res->t_energy = tm[0]; res->t_mmap = tm[1]; res->t_seam = tm[2];
+    rc = DCTC_OK;
+out:
+    dctc_lqr_carver_destroy(carver);
+    res->t_total = now_s() - t0;
+    if (rc != DCTC_OK) { double t = res->t_total; dctc_render_result_free(res); res->t_total = t; }
+    return rc;
+}

@@ -90,3 +90,50 @@ def test_per_pixel_symbol_serves_host_mirror(ctx):
     ctx.carve_and_update(np.full(30, 5, np.int32), want_band=False)
     en2 = ctx.carver_energy()
     assert L.dctc_pixel_energy(7, 9, 39, 30, None, C.byref(p)) == en2[9, 7]
+
+
+# ---- config 3: retarget through the host carver (liblqr stand-in) with GPU energy ---------------------------
+
+def _naive(img, b, e, t, n, energy):
+    from test_carver_cpu import naive_seams
+    return naive_seams(img, b, e, t, n, energy=energy)
+
+
+@pytest.mark.parametrize("b,wts", [(8, (0.5, 0.5)), (8, (0.8, 0.2)), (4, (0.5, 0.5)), (16, (0.5, 0.5))])
+def test_gpu_retarget_equals_naive_loop_fed_with_gpu_energy(ctx, b, wts):
+    """Incremental GPU energy (K2) + incremental cumulative map must give exactly the seams of the naive loop
+    that recomputes the full GPU energy map and the full DP for every seam."""
+    from dct_carver_b200 import host
+    img = ol.synth_image(150, 90, 3, 321 + b, 0)
+    ctx.set_params(b, *wts)
+    got = host.render(img, -25, b, *wts, ctx=ctx)
+    seams, out = _naive(img, b, *wts, 25, energy=lambda cur: ctx.energy_full(cur))
+    assert np.array_equal(got["seams"], seams)
+    assert np.array_equal(got["image"], out)
+    assert got["image"].shape == (90, 125, 3)
+
+
+def test_gpu_retarget_seams_vs_reference_energy(ctx):
+    """Seams chosen from the GPU (FP32) energies vs from the reference's double-precision energies: bit-exact until
+    a near-tie in the cumulative map flips (north_star: 'bit-exact wherever energy ties do not flip')."""
+    from dct_carver_b200 import host
+    img = ol.synth_image(160, 100, 3, 77, 0)
+    ctx.set_params(8, 0.5, 0.5)
+    got = host.render(img, -30, 8, 0.5, 0.5, ctx=ctx)
+    seams_ref, _ = _naive(img, 8, 0.5, 0.5, 30, energy=lambda cur: ol.best_energy(cur, 8, 0.5, 0.5))
+    same = [bool(np.array_equal(a, b)) for a, b in zip(got["seams"], seams_ref)]
+    lead = same.index(False) if False in same else len(same)
+    print("identical leading seams: %d / %d" % (lead, len(same)))
+    assert lead >= 1
+
+
+def test_gpu_retarget_height_and_energy_image(ctx):
+    from dct_carver_b200 import host
+    img = ol.synth_image(64, 70, 3, 9, 3)
+    ctx.set_params(8, 0.5, 0.5)
+    got = host.render(img, -6, 8, vertically=True, ctx=ctx, output_energy=True)
+    assert got["image"].shape == (64, 64, 3)
+    en = ctx.energy_full(img).astype(np.float32)
+    e = en / (1.0 + en)
+    want = np.floor(255.0 * (e - e.min()) / (e.max() - e.min()) + 0.5).astype(np.uint8)
+    assert np.abs(got["energy_image"].astype(int) - want.astype(int)).max() <= 1

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""BASELINE config 3: 1920x1080 RGB retarget to 75 % width (480 seams) through the host carver with incremental
+per-seam energy on the GPU (K2).  Reports us/seam and the split energy / cumulative map / seam search."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import dct_carver_b200 as dc  # noqa: E402
+from dct_carver_b200 import host  # noqa: E402
+import oracle_lib as ol  # noqa: E402  (synthetic image generator only)
+
+
+def main():
+    w, h, n = 1920, 1080, 480
+    if len(sys.argv) > 1:
+        n = int(sys.argv[1])
+    img = ol.synth_image(w, h, 3, 0xD0C7CA14, 0)
+    ctx = dc.Context(0)
+    host.render(img[:256, :256], -8, ctx=ctx)   # warm-up
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    r = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx)
+    dt = time.perf_counter() - t0
+    print(json.dumps({
+        "workload": "1920x1080 RGB -> %dx1080, %d vertical seams, blocksize 8" % (w - n, n),
+        "total_s": dt, "us_per_seam": 1e6 * dt / n, "seams_per_s": n / dt,
+        "energy_s (K1 full + K2 band incl. H2D/D2H)": r["t_energy"], "cumulative_map_s (host)": r["t_mmap"],
+        "seam_search_carve_s (host)": r["t_seam"], "gpu_launches": ctx.launches - l0,
+        "us_per_seam_energy": 1e6 * r["t_energy"] / n,
+    }))
+
+
+if __name__ == "__main__":
+    main()
