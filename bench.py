@@ -296,7 +296,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "gigapixel" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict({"workload": wl["desc"], "blocksize": args.blocksize, "edges": 0.5, "textures": 0.5,
                             "kernel": args.kernel, "l2": "inputs+outputs per step exceed L2 (distinct frames)",

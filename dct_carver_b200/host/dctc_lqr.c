@@ -8,7 +8,8 @@
 #include <time.h>
 
 struct DctcLqrCarver_ {
-    uint8_t *rgb;          /* current image, row pitch = w*ch (compacted after every seam) */
+    uint8_t *rgb;          /* current image, row pitch = pitch*ch (rows are compacted in place per seam) */
+    int pitch;             /* pixels per stored row (>= w) */
     int w, h, ch;
     int w_start, h_start;  /* size handed to lqr_carver_new */
     int transposed;
@@ -53,7 +54,7 @@ DctcLqrCarver *dctc_lqr_carver_new(uint8_t *buffer, int width, int height, int c
     r = (DctcLqrCarver *) calloc(1, sizeof(*r));
     if (!r) return NULL;
     r->rgb = buffer;
-    r->w = r->w_start = width;
+    r->w = r->w_start = r->pitch = width;
     r->h = r->h_start = height;
     r->ch = channels;
     r->delta_x = 1;
@@ -98,7 +99,7 @@ int dctc_lqr_carver_scan_line(DctcLqrCarver *r, int *n, uint8_t **rgb)
 {
     if (r->scan_pos >= r->h) { r->scan_pos = 0; return 0; }
     *n = r->scan_pos;
-    *rgb = r->rgb + (size_t) r->scan_pos * r->w * r->ch;
+    *rgb = r->rgb + (size_t) r->scan_pos * r->pitch * r->ch;
     r->scan_pos++;
     return 1;
 }
@@ -139,7 +140,7 @@ static void fill_luma(const DctcLqrCarver *r, double *luma)
 {
     int x, y;
     for (y = 0; y < r->h; y++)
-        for (x = 0; x < r->w; x++) luma[(size_t) y * r->w + x] = luma_px(r->rgb + ((size_t) y * r->w + x) * r->ch, r->ch);
+        for (x = 0; x < r->w; x++) luma[(size_t) y * r->w + x] = luma_px(r->rgb + ((size_t) y * r->pitch + x) * r->ch, r->ch);
 }
 
 static void band_limits(const int *seam, int y, int h, int w, int rad, int *xmin, int *xmax)
@@ -178,7 +179,7 @@ static int argmin_parent(const float *mrow_prev, int x, int w, int dx)
 /* removes k vertical seams from the current frame */
 static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
 {
-    const int P = r->w, h = r->h, ch = r->ch, dx = r->delta_x;
+    const int P = r->pitch, h = r->h, ch = r->ch, dx = r->delta_x;
     float *en = NULL, *m = NULL, *band = NULL;
     int *raw = NULL, *seam = NULL, *xmin = NULL, *xmax = NULL;
     double *luma = NULL;
@@ -209,7 +210,7 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
         free(r->vs);
         r->vs = (int *) calloc((size_t) P * h, sizeof(int));
         if (!r->vs) goto done;
-        r->vs_w = P; r->vs_h = h; r->vs_depth = 0;
+        r->vs_w = r->w; r->vs_h = h; r->vs_depth = 0;
     }
     for (y = 0; y < h; y++)
         for (x = 0; x < P; x++) raw[(size_t) y * P + x] = x;
@@ -218,15 +219,19 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
     t0 = now_s();
     rc = DCTC_LQR_ERROR;
     if (r->gpu) {
-        if (dctc_carver_load(r->gpu, r->rgb, r->w, h, ch, (size_t) r->w * ch) != DCTC_OK) goto done;
-        if (dctc_carver_energy(r->gpu, en) != DCTC_OK) goto done;
+        float *tmp = (float *) malloc(sizeof(float) * (size_t) r->w * h);
+        if (!tmp) { rc = DCTC_LQR_NOMEM; goto done; }
+        if (dctc_carver_load(r->gpu, r->rgb, r->w, h, ch, (size_t) P * ch) != DCTC_OK ||
+            dctc_carver_energy(r->gpu, tmp) != DCTC_OK) { free(tmp); goto done; }
+        for (y = 0; y < h; y++) memcpy(en + (size_t) y * P, tmp + (size_t) y * r->w, sizeof(float) * r->w);
+        free(tmp);
     } else {
         fill_luma(r, luma);
         rw.luma = luma; rw.w = r->w; rw.h = h; rw.radius = r->radius;
         for (y = 0; y < h; y++)
             for (x = 0; x < r->w; x++) {
                 rw.x = x; rw.y = y;
-                en[(size_t) y * r->w + x] = r->nrg(x, y, r->w, h, &rw, r->extra);
+                en[(size_t) y * P + x] = r->nrg(x, y, r->w, h, &rw, r->extra);
             }
     }
     r->timing[0] += now_s() - t0;
@@ -236,7 +241,7 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
     memcpy(m, en, sizeof(float) * r->w);
     for (y = 1; y < h; y++)
         for (x = 0; x < r->w; x++)
-            m[(size_t) y * r->w + x] = en[(size_t) y * r->w + x] + min_parent(m + (size_t) (y - 1) * r->w, x, r->w, dx);
+            m[(size_t) y * P + x] = en[(size_t) y * P + x] + min_parent(m + (size_t) (y - 1) * P, x, r->w, dx);
     r->timing[1] += now_s() - t0;
 
     for (s = 0; s < k; s++) {
@@ -245,27 +250,23 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
         /* build_vpath: leftmost minimum of the last row, then back-track */
         t0 = now_s();
         {
-            const float *last = m + (size_t) (h - 1) * w;
+            const float *last = m + (size_t) (h - 1) * P;
             int best = 0;
             for (x = 1; x < w; x++)
                 if (last[x] < last[best]) best = x;
             seam[h - 1] = best;
-            for (y = h - 1; y > 0; y--) seam[y - 1] = argmin_parent(m + (size_t) (y - 1) * w, seam[y], w, dx);
+            for (y = h - 1; y > 0; y--) seam[y - 1] = argmin_parent(m + (size_t) (y - 1) * P, seam[y], w, dx);
         }
         memcpy(r->seams + (size_t) r->n_seams * h, seam, sizeof(int) * h);
         r->n_seams++;
-        /* update_vsmap + carve: compact rgb, raw, en, m from pitch w to pitch w-1 */
+        /* update_vsmap + carve: shift the tail of every row one pixel to the left (pitch stays P) */
         for (y = 0; y < h; y++) {
-            const int sx = seam[y];
-            if (record_vs) r->vs[(size_t) y * P + raw[(size_t) y * w + sx]] = r->vs_depth + 1;
-            memmove(r->rgb + (size_t) y * w1 * ch, r->rgb + (size_t) y * w * ch, (size_t) sx * ch);
-            memmove(r->rgb + ((size_t) y * w1 + sx) * ch, r->rgb + ((size_t) y * w + sx + 1) * ch, (size_t) (w1 - sx) * ch);
-            memmove(raw + (size_t) y * w1, raw + (size_t) y * w, sizeof(int) * sx);
-            memmove(raw + (size_t) y * w1 + sx, raw + (size_t) y * w + sx + 1, sizeof(int) * (w1 - sx));
-            memmove(en + (size_t) y * w1, en + (size_t) y * w, sizeof(float) * sx);
-            memmove(en + (size_t) y * w1 + sx, en + (size_t) y * w + sx + 1, sizeof(float) * (w1 - sx));
-            memmove(m + (size_t) y * w1, m + (size_t) y * w, sizeof(float) * sx);
-            memmove(m + (size_t) y * w1 + sx, m + (size_t) y * w + sx + 1, sizeof(float) * (w1 - sx));
+            const int sx = seam[y], tail = w1 - sx;
+            if (record_vs) r->vs[(size_t) y * r->vs_w + raw[(size_t) y * P + sx]] = r->vs_depth + 1;
+            memmove(r->rgb + ((size_t) y * P + sx) * ch, r->rgb + ((size_t) y * P + sx + 1) * ch, (size_t) tail * ch);
+            memmove(raw + (size_t) y * P + sx, raw + (size_t) y * P + sx + 1, sizeof(int) * tail);
+            memmove(en + (size_t) y * P + sx, en + (size_t) y * P + sx + 1, sizeof(float) * tail);
+            memmove(m + (size_t) y * P + sx, m + (size_t) y * P + sx + 1, sizeof(float) * tail);
         }
         if (record_vs) r->vs_depth++;
         r->w = w1;
@@ -278,7 +279,7 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
             if (dctc_carve_and_update(r->gpu, seam, band, xmin, xmax) != DCTC_OK) { rc = DCTC_LQR_ERROR; goto done; }
             for (y = 0; y < h; y++) {
                 const int n = xmax[y] - xmin[y] + 1;
-                if (n > 0) { memcpy(en + (size_t) y * w1 + xmin[y], band + off, sizeof(float) * n); off += n; }
+                if (n > 0) { memcpy(en + (size_t) y * P + xmin[y], band + off, sizeof(float) * n); off += n; }
             }
         } else {
             fill_luma(r, luma);
@@ -287,7 +288,7 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
                 band_limits(seam, y, h, w1, r->radius, &xmin[y], &xmax[y]);
                 for (x = xmin[y]; x <= xmax[y]; x++) {
                     rw.x = x; rw.y = y;
-                    en[(size_t) y * w1 + x] = r->nrg(x, y, w1, h, &rw, r->extra);
+                    en[(size_t) y * P + x] = r->nrg(x, y, w1, h, &rw, r->extra);
                 }
             }
         }
@@ -297,8 +298,8 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
          * cells whose value actually changed (cone of delta_x per row); identical to a full rebuild */
         t0 = now_s();
         for (y = 0; y < h; y++) {
-            float *mrow = m + (size_t) y * w1;
-            const float *erow = en + (size_t) y * w1;
+            float *mrow = m + (size_t) y * P;
+            const float *erow = en + (size_t) y * P;
             int lo = xmin[y], hi = xmax[y], nlo = w1, nhi = -1;
             if (y > 0) {
                 const int s0 = seam[y - 1] < seam[y] ? seam[y - 1] : seam[y];
@@ -313,7 +314,7 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
             if (lo < 0) lo = 0;
             if (hi > w1 - 1) hi = w1 - 1;
             for (x = lo; x <= hi; x++) {
-                const float v = y == 0 ? erow[x] : erow[x] + min_parent(mrow - w1, x, w1, dx);
+                const float v = y == 0 ? erow[x] : erow[x] + min_parent(mrow - P, x, w1, dx);
                 if (v != mrow[x]) {
                     mrow[x] = v;
                     if (x < nlo) nlo = x;
@@ -324,6 +325,8 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
         }
         r->timing[1] += now_s() - t0;
     }
+    for (y = 1; y < h; y++) memmove(r->rgb + (size_t) y * r->w * ch, r->rgb + (size_t) y * P * ch, (size_t) r->w * ch);
+    r->pitch = r->w;
     rc = DCTC_LQR_OK;
 done:
     free(en); free(m); free(raw); free(seam); free(xmin); free(xmax); free(band); free(luma);
@@ -337,9 +340,9 @@ static int transpose(DctcLqrCarver *r)
     uint8_t *t = (uint8_t *) malloc((size_t) w * h * ch);
     if (!t) return DCTC_LQR_NOMEM;
     for (y = 0; y < h; y++)
-        for (x = 0; x < w; x++) memcpy(t + ((size_t) x * h + y) * ch, r->rgb + ((size_t) y * w + x) * ch, ch);
+        for (x = 0; x < w; x++) memcpy(t + ((size_t) x * h + y) * ch, r->rgb + ((size_t) y * r->pitch + x) * ch, ch);
     free(r->rgb);
-    r->rgb = t; r->w = h; r->h = w;
+    r->rgb = t; r->w = r->pitch = h; r->h = w;
     r->transposed = !r->transposed;
     return DCTC_LQR_OK;
 }
@@ -372,7 +375,7 @@ int dctc_lqr_carver_get_energy(DctcLqrCarver *r, float *buffer)
     int x, y;
     if (!r || !buffer) return DCTC_LQR_ERROR;
     if (r->gpu) {
-        if (dctc_carver_load(r->gpu, r->rgb, r->w, r->h, r->ch, (size_t) r->w * r->ch) != DCTC_OK) return DCTC_LQR_ERROR;
+        if (dctc_carver_load(r->gpu, r->rgb, r->w, r->h, r->ch, (size_t) r->pitch * r->ch) != DCTC_OK) return DCTC_LQR_ERROR;
         return dctc_carver_energy(r->gpu, buffer) == DCTC_OK ? DCTC_LQR_OK : DCTC_LQR_ERROR;
     }
     if (!r->nrg) return DCTC_LQR_ERROR;
