@@ -152,12 +152,18 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
     fill_weights(ctx, a);
     const bool uniform = ctx->edges == ctx->textures;
     int kernel = ctx->kernel;
-    if (kernel == DCTC_KERNEL_AUTO) kernel = DCTC_KERNEL_FP32_TILE;
-    if (kernel != DCTC_KERNEL_FP32_TILE && ctx->blocksize != 8) return DCTC_ERR_UNSUPPORTED;
+    // band mode (per-seam update) always runs in the tile kernel; block size 8 full maps default to the march kernel
+    if (a.seam || ctx->blocksize != 8) {
+        if (kernel != DCTC_KERNEL_AUTO && kernel != DCTC_KERNEL_FP32_TILE && !a.seam) return DCTC_ERR_UNSUPPORTED;
+        kernel = DCTC_KERNEL_FP32_TILE;
+    } else if (kernel == DCTC_KERNEL_AUTO) {
+        kernel = DCTC_KERNEL_FP32_MARCH;
+    }
     cudaError_t e;
     switch (kernel) {
     case DCTC_KERNEL_FP32_TILE: e = dctc_launch_k1_tile(a, ctx->blocksize, n_frames, uniform, stream); break;
-    default: return DCTC_ERR_UNSUPPORTED;
+    case DCTC_KERNEL_FP32_MARCH: e = dctc_launch_k1_march8(a, n_frames, uniform, stream); break;
+    default: return DCTC_ERR_UNSUPPORTED;  // DCTC_KERNEL_TC_SPLIT: measured not competitive, see profiles/r01_tcgen05_probe.txt
     }
     if (e != cudaSuccess) return dctc_fail_cuda(ctx, e);
     ctx->launches++;

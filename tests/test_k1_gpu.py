@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "energy_golden.npz"))
 N_GOLD = sum(1 for k in GOLD.files if k.startswith("img_"))
-KERNELS = [dc.KERNEL_FP32_TILE]
+KERNELS = [dc.KERNEL_FP32_TILE, dc.KERNEL_FP32_MARCH]
 
 
 def check_with_flips(got, img, b, e, t, max_flip_frac=2e-3):
