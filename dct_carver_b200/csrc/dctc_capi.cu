@@ -163,7 +163,12 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
     switch (kernel) {
     case DCTC_KERNEL_FP32_TILE: e = dctc_launch_k1_tile(a, ctx->blocksize, n_frames, uniform, stream); break;
     case DCTC_KERNEL_FP32_MARCH: e = dctc_launch_k1_march8(a, n_frames, uniform, stream); break;
-    default: return DCTC_ERR_UNSUPPORTED;  // DCTC_KERNEL_TC_SPLIT: measured not competitive, see profiles/r01_tcgen05_probe.txt
+    case DCTC_KERNEL_TC_SPLIT:
+        e = dctc_launch_k1_tc8(a, n_frames, uniform, stream);
+        // outside the tensor-core fast path (channel count / alignment): same operator on the FP32 march kernel
+        if (e == cudaErrorNotSupported) e = dctc_launch_k1_march8(a, n_frames, uniform, stream);
+        break;
+    default: return DCTC_ERR_UNSUPPORTED;
     }
     if (e != cudaSuccess) return dctc_fail_cuda(ctx, e);
     ctx->launches++;
