@@ -73,6 +73,8 @@ int dctc_create(dctc_context** out, int device)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc((void**) &ctx->tc_counters, DCTC_TC_COUNTERS * sizeof(int));
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t1);
     for (int i = 0; i < DCTC_SLOTS && e == cudaSuccess; i++) {
@@ -104,6 +106,7 @@ void dctc_destroy(dctc_context* ctx)
         if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
         if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     }
+    if (ctx->tc_counters) cudaFree(ctx->tc_counters);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -164,7 +167,8 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
     case DCTC_KERNEL_FP32_TILE: e = dctc_launch_k1_tile(a, ctx->blocksize, n_frames, uniform, stream); break;
     case DCTC_KERNEL_FP32_MARCH: e = dctc_launch_k1_march8(a, n_frames, uniform, stream); break;
     case DCTC_KERNEL_TC_SPLIT:
-        e = dctc_launch_k1_tc8(a, n_frames, uniform, stream);
+        // every launch takes its own work-item counter, so launches in flight on different streams never share one
+        e = dctc_launch_k1_tc8(a, n_frames, uniform, ctx->tc_counters + (ctx->tc_next++ % DCTC_TC_COUNTERS), ctx->sm_count, stream);
         // outside the tensor-core fast path (channel count / alignment): same operator on the FP32 march kernel
         if (e == cudaErrorNotSupported) e = dctc_launch_k1_march8(a, n_frames, uniform, stream);
         break;

@@ -19,6 +19,7 @@
 // Per pixel the CUDA cores execute ~100 instructions instead of the ~264 of the FP32 march kernel; the tensor pipe
 // does 24 M128 N64 K16 MMAs per 1024 pixels (36.3 clk each measured, profiles/r01_tcgen05_probe2.txt).
 #include <cuda_fp16.h>
+#include <cstdio>
 #include "dctc_common.cuh"
 #include "dctc_launch.h"
 #include "dctc_tc_tables.cuh"
@@ -45,25 +46,49 @@ struct alignas(128) TcSmem {
     uint8_t Raw[2][8 * RawGeom<3>::ROW];
     uint64_t bar_a_full, bar_a_free, bar_d_full[2], bar_d_free[2];
     uint32_t tmem_base;
+    int work;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_inval(uint32_t bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+// Tight parity wait (labels are local to the braces).  try_wait suspends the warp in hardware for a bounded time per
+// attempt; after 2^22 failed attempts (seconds) a protocol error traps, so the launch fails instead of hanging.
+#ifdef DCTC_TC_DEBUG
+__device__ __noinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0)
 {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
+    for (uint32_t n = 0;; n++) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (n > (1u << 20)) { printf("mbar timeout tag %d parity %u block %d thread %d\n", tag, parity, blockIdx.x, threadIdx.x); __trap(); }
+    }
 }
-// Bounded spin: a protocol error traps (the launch fails with an error) instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+#else
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0)
 {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity))
-        if (clock64() - t0 > (1LL << 31)) __trap();   // ~1 s
+    (void) tag;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "DCTC_WAIT:\n"
+#if DCTC_TC_WAITMODE == 1
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
+        "@p bra DCTC_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 0x400000;\n"
+        "@p bra DCTC_WAIT;\n"
+        "trap;\n"
+        "DCTC_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
 }
+#endif
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -190,9 +215,10 @@ __device__ __forceinline__ void produce_group(TcSmem& s, int g, int tid, uint32_
             tmem_st_x2(ta + (uint32_t) (k1 * 16 + 8 + half * 2), lo[k1][0], lo[k1][1]);
         }
     }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // warp-wide: every lane's stores have completed
     tc_fence_before();
-    mbar_arrive(smem_u32(&s.bar_a_full));
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(smem_u32(&s.bar_a_full));        // one arrival per producer warp
 }
 
 // ---- consumer fold -------------------------------------------------------------------------------------------
@@ -259,7 +285,7 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
 };
 
 template <int K1, bool UNIFORM>
-__device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32_t tmem_lane)
+__device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32_t tmem_lane, bool lane0)
 {
     constexpr int b = K1 & 1, q = K1 >> 1;
     mbar_wait(smem_u32(&s.bar_d_full[b]), (uint32_t) (q & 1));
@@ -267,34 +293,24 @@ __device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32
     uint32_t v[64];
     tmem_ld_x64(tmem_lane + TM_D + 64u * b, v);
     tc_fence_before();
-    mbar_arrive(smem_u32(&s.bar_d_free[b]));
+    __syncwarp();
+    if (lane0) mbar_arrive(smem_u32(&s.bar_d_free[b]));               // one arrival per consumer warp
     f.template add<K1>(v);
 }
 
+// Persistent kernel: two CTAs per SM (256 TMEM columns each), work items = (frame, segment, strip) handed out by an
+// atomic counter.
 template <bool UNIFORM, int CH>
-__global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Args a, int seg_rows)
+__global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Args a, int seg_rows, int strips, int segs, int n_items,
+                                                                    int* __restrict__ counter)
 {
     __shared__ TcSmem s;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int x0 = blockIdx.x * MW;
-    const int y0 = blockIdx.y * seg_rows;
-    const int y1 = min(y0 + seg_rows, a.h);
-    const int nsteps = (y1 - y0 + 7) >> 3;
-    const uint8_t* __restrict__ img = a.img + (size_t) blockIdx.z * a.frame_stride;
-    float* __restrict__ out = a.out + (size_t) blockIdx.z * a.out_frame_stride;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 0) {
-        mbar_init(smem_u32(&s.bar_a_full), 128);
-        mbar_init(smem_u32(&s.bar_a_free), 1);
-        mbar_init(smem_u32(&s.bar_d_full[0]), 1);
-        mbar_init(smem_u32(&s.bar_d_full[1]), 1);
-        mbar_init(smem_u32(&s.bar_d_free[0]), 128);
-        mbar_init(smem_u32(&s.bar_d_free[1]), 128);
-        asm volatile("fence.mbarrier_init.release.cluster;");
     }
     // Toeplitz operands: Tz[n = i*8 + k2][k] = B8[k2][r - i] with window row r = k (normal) or k ^ 8 (K-swapped)
     {
@@ -308,11 +324,45 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t lane_off = (uint32_t) ((warp & 3) * 32) << 16;
+    bool first = true;
+
+  for (;;) {
+    if (tid == 0) {
+        s.work = atomicAdd(counter, 1);
+        if (!first) {
+            mbar_inval(smem_u32(&s.bar_a_full));
+            mbar_inval(smem_u32(&s.bar_a_free));
+            mbar_inval(smem_u32(&s.bar_d_full[0]));
+            mbar_inval(smem_u32(&s.bar_d_full[1]));
+            mbar_inval(smem_u32(&s.bar_d_free[0]));
+            mbar_inval(smem_u32(&s.bar_d_free[1]));
+        }
+        mbar_init(smem_u32(&s.bar_a_full), 4);
+        mbar_init(smem_u32(&s.bar_a_free), 1);
+        mbar_init(smem_u32(&s.bar_d_full[0]), 1);
+        mbar_init(smem_u32(&s.bar_d_full[1]), 1);
+        mbar_init(smem_u32(&s.bar_d_free[0]), 4);
+        mbar_init(smem_u32(&s.bar_d_free[1]), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    first = false;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    const int item = s.work;
+    if (item >= n_items) break;
     const uint32_t tmem = s.tmem_base;
-    const uint32_t tmem_lane = tmem + ((uint32_t) ((warp & 3) * 32) << 16);
+    const uint32_t tmem_lane = tmem + lane_off;
+    const int strip = item % strips;
+    const int rest = item / strips;
+    const int seg = rest % segs, frame = rest / segs;
+    const int x0 = strip * MW;
+    const int y0 = seg * seg_rows;
+    const int y1 = min(y0 + seg_rows, a.h);
+    const int nsteps = (y1 - y0 + 7) >> 3;
+    const uint8_t* __restrict__ img = a.img + (size_t) frame * a.frame_stride;
+    float* __restrict__ out = a.out + (size_t) frame * a.out_frame_stride;
 
     if (warp < 4) {
         // ===== producers: group g = virtual rows y0-3+8g .. y0+4+8g; step j consumes groups j and j+1 =====
@@ -335,22 +385,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         // ===== consumers =====
         const int px = tid - 128;
         const int gx = x0 + px;
+        const bool lane0 = (tid & 31) == 0;
         for (int st = 0; st < nsteps; st++) {
             TcFold<UNIFORM> f;
             f.init();
-            consume_k1<0, UNIFORM>(s, f, tmem_lane);
-            consume_k1<1, UNIFORM>(s, f, tmem_lane);
-            consume_k1<2, UNIFORM>(s, f, tmem_lane);
-            consume_k1<3, UNIFORM>(s, f, tmem_lane);
-            consume_k1<4, UNIFORM>(s, f, tmem_lane);
-            consume_k1<5, UNIFORM>(s, f, tmem_lane);
-            consume_k1<6, UNIFORM>(s, f, tmem_lane);
-            consume_k1<7, UNIFORM>(s, f, tmem_lane);
+            consume_k1<0, UNIFORM>(s, f, tmem_lane, lane0);
+            consume_k1<1, UNIFORM>(s, f, tmem_lane, lane0);
+            consume_k1<2, UNIFORM>(s, f, tmem_lane, lane0);
+            consume_k1<3, UNIFORM>(s, f, tmem_lane, lane0);
+            consume_k1<4, UNIFORM>(s, f, tmem_lane, lane0);
+            consume_k1<5, UNIFORM>(s, f, tmem_lane, lane0);
+            consume_k1<6, UNIFORM>(s, f, tmem_lane, lane0);
+            consume_k1<7, UNIFORM>(s, f, tmem_lane, lane0);
             const int gy = y0 + 8 * st;
             if (gx < a.w) {
+                float* __restrict__ o = out + (size_t) gy * a.out_pitch + gx;
+                if (gy + 8 <= y1) {
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-                    if (gy + i < y1) out[(size_t) (gy + i) * a.out_pitch + gx] = f.result(i, a.w_edges, a.w_textures);
+                    for (int i = 0; i < 8; i++) o[(size_t) i * a.out_pitch] = f.result(i, a.w_edges, a.w_textures);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (gy + i < y1) o[(size_t) i * a.out_pitch] = f.result(i, a.w_edges, a.w_textures);
+                }
             }
         }
     } else {
@@ -377,43 +434,49 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
                     mma_ts(d, ah, bl, idesc, 1u);
                     mma_commit(smem_u32(&s.bar_d_full[b]));
                 }
-                mma_commit(smem_u32(&s.bar_a_free));
+                if (st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free));   // waited on by the producers of group st+2
             }
             __syncwarp();
         }
     }
-
     tc_fence_before();
-    __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    __syncthreads();    // every role is done with the barriers, TMEM and staging buffers of this item
+  }
+
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "r"(TMEM_COLS));
 }
 
 }  // namespace
 
 // Returns cudaErrorNotSupported when the configuration is outside this kernel's fast path (the caller then uses
 // the FP32 march kernel): needs 1 or 3 channels and 16-byte aligned row pointers / pitches.
-cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, cudaStream_t stream)
+// `counter` is a device int owned by the context (work-item counter of the persistent kernel).
+cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, int* counter, int sm_count, cudaStream_t stream)
 {
     if (a.w <= 0 || a.h <= 0 || n_frames <= 0) return cudaSuccess;
     if (a.seam) return cudaErrorInvalidValue;  // band mode lives in the tile kernel
     auto aligned16 = [](const void* p, size_t pitch) { return (((uintptr_t) p | pitch) & 15) == 0; };
     const bool fast = (a.channels == 3 || a.channels == 1) && aligned16(a.img, a.pitch) && (a.frame_stride & 15) == 0 &&
                       (!a.top || aligned16(a.top, a.top_pitch)) && (!a.bot || aligned16(a.bot, a.bot_pitch));
-    if (!fast) return cudaErrorNotSupported;
+    if (!fast || !counter) return cudaErrorNotSupported;
     const int strips = (a.w + MW - 1) / MW;
-    int seg = 256;
-    while (seg > 16 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 2LL * 148 * 2) seg >>= 1;
+    // segment height: long segments amortise the 8-row prologue; keep >= ~6 items per SM so the tail stays short
+    int seg = 512;
+    while (seg > 32 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 12LL * sm_count) seg >>= 1;
     const int segs = (a.h + seg - 1) / seg;
-    if (segs > 65535 || n_frames > 65535) return cudaErrorInvalidConfiguration;
-    dim3 grid(strips, segs, n_frames), block(NTHREADS);
-#define DCTC_TC_LAUNCH(U, C, SLOT)                                                                                     \
+    const long long items = (long long) strips * segs * n_frames;
+    if (items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const int grid = (int) (items < 2LL * sm_count ? items : 2LL * sm_count);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+#define DCTC_TC_LAUNCH(U, C)                                                                                           \
     do {                                                                                                               \
         cudaError_t ea = cudaFuncSetAttribute(dctc_k1_tc8_kernel<U, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAD_SMEM); \
         if (ea != cudaSuccess) return ea;                                                                              \
-        dctc_k1_tc8_kernel<U, C><<<grid, block, PAD_SMEM, stream>>>(a, seg);                                           \
+        dctc_k1_tc8_kernel<U, C><<<grid, NTHREADS, PAD_SMEM, stream>>>(a, seg, strips, segs, (int) items, counter);    \
     } while (0)
-    if (a.channels == 3) { if (uniform) DCTC_TC_LAUNCH(true, 3, 0); else DCTC_TC_LAUNCH(false, 3, 1); }
-    else { if (uniform) DCTC_TC_LAUNCH(true, 1, 2); else DCTC_TC_LAUNCH(false, 1, 3); }
+    if (a.channels == 3) { if (uniform) DCTC_TC_LAUNCH(true, 3); else DCTC_TC_LAUNCH(false, 3); }
+    else { if (uniform) DCTC_TC_LAUNCH(true, 1); else DCTC_TC_LAUNCH(false, 1); }
 #undef DCTC_TC_LAUNCH
     return cudaGetLastError();
 }

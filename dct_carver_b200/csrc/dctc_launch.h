@@ -9,12 +9,13 @@ struct DctcK1Args;
 
 cudaError_t dctc_launch_k1_tile(const DctcK1Args& a, int blocksize, int n_frames, bool uniform, cudaStream_t stream);
 cudaError_t dctc_launch_k1_march8(const DctcK1Args& a, int n_frames, bool uniform, cudaStream_t stream);
-cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, cudaStream_t stream);
+cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, int* counter, int sm_count, cudaStream_t stream);
 cudaError_t dctc_launch_synth(uint8_t* d_img, int n_frames, size_t frame_stride, int w, int h, int channels,
                               size_t pitch, uint32_t seed, int pattern, int first_frame, int y_offset,
                               cudaStream_t stream);
 
 constexpr int DCTC_SLOTS = 3;
+constexpr int DCTC_TC_COUNTERS = 64;
 
 struct dctc_context {
     int device = 0;
@@ -28,6 +29,9 @@ struct dctc_context {
     int kernel = DCTC_KERNEL_AUTO;
     int last_cuda = 0;
     unsigned long long launches = 0;
+    int sm_count = 0;
+    int* tc_counters = nullptr;         // work-item counters of the persistent tensor-core kernel (device)
+    unsigned tc_next = 0;
     // staging slots of the host-buffer API
     uint8_t* d_in[DCTC_SLOTS] = {};
     float* d_out[DCTC_SLOTS] = {};

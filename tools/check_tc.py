@@ -22,7 +22,11 @@ def main():
             img = ol.synth_image(w, h, ch, 1234, pattern)
             ctx.set_params(8, *wts)
             ctx.set_kernel(dc.KERNEL_TC_SPLIT)
-            got = ctx.energy_full(img)
+            try:
+                got = ctx.energy_full(img)
+            except dc.DctcError:
+                print("CUDA error code", dc.lib().dctc_last_cuda_error(ctx.handle))
+                raise
             ctx.set_kernel(dc.KERNEL_FP32_MARCH)
             ref32 = ctx.energy_full(img)
             want = ol.oracle_energy(img, 8, *wts) if w * h <= 700 * 400 else ref32
