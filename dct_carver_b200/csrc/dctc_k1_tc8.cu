@@ -98,6 +98,10 @@ __device__ __forceinline__ bool elect_one()
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Accumulator tile t is handed back to the MMA warp through hardware named barrier 2+t (4 consumer warps arrive, the
+// MMA warp syncs: 160 threads): the wake-up is immediate, unlike polling an mbarrier from the issuing thread.
+__device__ __forceinline__ void bar_tile_arrive(int t) { asm volatile("bar.arrive %0, 160;" ::"r"(2 + t) : "memory"); }
+__device__ __forceinline__ void bar_tile_sync(int t) { asm volatile("bar.sync %0, 160;" ::"r"(2 + t) : "memory"); }
 
 // shared-memory matrix descriptor, no swizzle, K-major: LBO = byte stride between core matrices along K,
 // SBO = byte stride between 8-row groups along N (validated by tools/tc_probe.cu)
@@ -218,7 +222,9 @@ __device__ __forceinline__ void produce_group(TcSmem& s, int g, int tid, uint32_
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // warp-wide: every lane's stores have completed
     tc_fence_before();
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(smem_u32(&s.bar_a_full));        // one arrival per producer warp
+    // Group 0 is not announced on its own: the arrival of group 1 covers both (same warp, program order), so the MMA
+    // warp needs exactly one parity wait per step and can never be two phases behind the producers.
+    if (g >= 1 && (tid & 31) == 0) mbar_arrive(smem_u32(&s.bar_a_full));   // one arrival per producer warp
 }
 
 // ---- consumer fold -------------------------------------------------------------------------------------------
@@ -293,8 +299,8 @@ __device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32
     uint32_t v[64];
     tmem_ld_x64(tmem_lane + TM_D + 64u * b, v);
     tc_fence_before();
-    __syncwarp();
-    if (lane0) mbar_arrive(smem_u32(&s.bar_d_free[b]));               // one arrival per consumer warp
+    (void) lane0;
+    bar_tile_arrive(b);
     f.template add<K1>(v);
 }
 
@@ -414,30 +420,33 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc(128, 64);
         const uint64_t bd0 = make_smem_desc(smem_u32(&s.B[0][0]), 128, 256);
-        mbar_wait(smem_u32(&s.bar_a_full), 0u);                              // group 0 is in TMEM
         for (int st = 0; st < nsteps; st++) {
-            mbar_wait(smem_u32(&s.bar_a_full), (uint32_t) ((st + 1) & 1));   // group st+1 is in TMEM (one wait per completion)
+            mbar_wait(smem_u32(&s.bar_a_full), (uint32_t) (st & 1));         // groups st and st+1 are in TMEM
             tc_fence_after();
-            if (elect_one()) {
-                // each operand copy is 2048 bytes = 128 descriptor address units
-                const uint64_t bh = bd0 + (uint64_t) ((st & 1) ? 256 : 0);
-                const uint64_t bl = bh + 128;
+            // each operand copy is 2048 bytes = 128 descriptor address units
+            const uint64_t bh = bd0 + (uint64_t) ((st & 1) ? 256 : 0);
+            const uint64_t bl = bh + 128;
 #pragma unroll
-                for (int k1 = 0; k1 < 8; k1++) {
-                    const int b = k1 & 1, q = k1 >> 1;
-                    mbar_wait(smem_u32(&s.bar_d_free[b]), (uint32_t) ((q + 1) & 1));
-                    tc_fence_after();
+            for (int k1 = 0; k1 < 8; k1++) {
+                const int b = k1 & 1;
+                if (st > 0 || k1 >= 2) bar_tile_sync(b);     // the consumers have loaded the previous contents of tile b
+                tc_fence_after();
+                if (elect_one()) {
                     const uint32_t d = tmem + TM_D + 64u * b;
                     const uint32_t ah = tmem + TM_A + (uint32_t) k1 * 16u, al = ah + 8u;
                     mma_ts(d, ah, bh, idesc, 0u);
                     mma_ts(d, al, bh, idesc, 1u);
                     mma_ts(d, ah, bl, idesc, 1u);
                     mma_commit(smem_u32(&s.bar_d_full[b]));
+                    if (k1 == 7 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free));   // waited on by the producers of group st+2
                 }
-                if (st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free));   // waited on by the producers of group st+2
+                __syncwarp();
             }
-            __syncwarp();
         }
+        // the last use of each tile was arrived on but never waited for: drain both named barriers so that their
+        // generations start clean for the next work item
+        bar_tile_sync(0);
+        bar_tile_sync(1);
     }
     tc_fence_before();
     __syncthreads();    // every role is done with the barriers, TMEM and staging buffers of this item
