@@ -155,12 +155,12 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
     fill_weights(ctx, a);
     const bool uniform = ctx->edges == ctx->textures;
     int kernel = ctx->kernel;
-    // band mode (per-seam update) always runs in the tile kernel; block size 8 full maps default to the march kernel
+    // band mode (per-seam update) always runs in the tile kernel; block size 8 full maps default to the tensor-core
+    // kernel (which hands configurations outside its fast path to the FP32 march kernel)
     if (a.seam || ctx->blocksize != 8) {
-        if (kernel != DCTC_KERNEL_AUTO && kernel != DCTC_KERNEL_FP32_TILE && !a.seam) return DCTC_ERR_UNSUPPORTED;
-        kernel = DCTC_KERNEL_FP32_TILE;
+        kernel = DCTC_KERNEL_FP32_TILE;   // the kernel choice (dctc_set_kernel) only concerns block size 8 full maps
     } else if (kernel == DCTC_KERNEL_AUTO) {
-        kernel = DCTC_KERNEL_FP32_MARCH;
+        kernel = DCTC_KERNEL_TC_SPLIT;
     }
     cudaError_t e;
     switch (kernel) {

@@ -112,7 +112,13 @@ int dctc_carver_load(dctc_context* ctx, const uint8_t* img, int w, int h, int ch
                               ctx->stream));
     DctcK1Args a;
     carver_args(ctx, a);
+    // A carver session keeps one arithmetic for the whole seam loop: the per-seam band updates run in the FP32 tile
+    // kernel, so the initial full map uses the bit-identical FP32 march kernel rather than the tensor-core kernel
+    // (liblqr: update_emap must reproduce what build_emap would give on the carved image).
+    const int saved_kernel = ctx->kernel;
+    if (ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_TC_SPLIT) ctx->kernel = DCTC_KERNEL_FP32_MARCH;
     int rc = dctc_run_k1(ctx, a, 1, ctx->stream);
+    ctx->kernel = saved_kernel;
     if (rc) return rc;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return DCTC_OK;

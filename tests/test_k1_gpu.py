@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "energy_golden.npz"))
 N_GOLD = sum(1 for k in GOLD.files if k.startswith("img_"))
-KERNELS = [dc.KERNEL_FP32_TILE, dc.KERNEL_FP32_MARCH]
+KERNELS = [dc.KERNEL_FP32_TILE, dc.KERNEL_FP32_MARCH, dc.KERNEL_TC_SPLIT]
 
 
 def check_with_flips(got, img, b, e, t, max_flip_frac=2e-3):
@@ -155,10 +155,28 @@ def _band_run(ctx, img, bounds, b):
 
 @pytest.mark.parametrize("b", [2, 4, 8, 16])
 def test_row_bands_with_halo_equal_full_image(ctx, b):
+    """Row bands + halos reproduce the full map BIT-exactly when one kernel serves both (the FP32 kernels here; rows
+    of a 150-px RGB image are not 16-byte aligned, which is outside the tensor-core kernel's fast path)."""
     img = ol.synth_image(150, 101, 3, 7, 0)
     ctx.set_params(b, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_FP32_MARCH)
     full = ctx.energy_full(img)
     got = _band_run(ctx, img, [(0, 13), (13, 50), (50, 51), (51, 101)], b)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    assert np.array_equal(got, full)
+
+
+@pytest.mark.parametrize("ch,w", [(3, 160), (1, 208)])
+def test_row_bands_tensor_core_kernel(ctx, ch, w):
+    """Same property through the tensor-core kernel (16-byte aligned rows, so every band stays on its fast path):
+    the band decomposition changes which ring slot / MMA step a row falls into, and the result must not depend on it."""
+    img = ol.synth_image(w, 131, ch, 17, 0)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_TC_SPLIT)
+    full = ctx.energy_full(img)
+    got = _band_run(ctx, img, [(0, 13), (13, 50), (50, 51), (51, 131)], 8)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    ol.assert_parity(got, ol.best_energy(img, 8, 0.5, 0.5))
     assert np.array_equal(got, full)
 
 

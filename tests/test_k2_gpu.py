@@ -10,7 +10,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def ctx():
-    c = dc.Context(0)
+    # A carver session runs in one arithmetic (FP32 march + FP32 tile kernels, bit-identical to each other); the
+    # "full recompute" references below therefore pin the FP32 march kernel instead of AUTO (= tensor cores).
+    c = dc.Context(0, kernel=dc.KERNEL_FP32_MARCH)
     yield c
     c.close()
 
