@@ -280,6 +280,15 @@ class Context:
         _check(lib().dctc_carver_image(self._h, _ptr(out)), "dctc_carver_image")
         return out
 
+    def carver_resize_width(self, n_seams):
+        """Whole retarget loop on the device (seam DP, back-track, carve, band energy update per seam); returns the
+        removed columns, shape (n_seams, h), in the coordinates of the image at the time of removal."""
+        w, h = self.carver_size()
+        seams = np.empty((n_seams, h), np.int32)
+        _check(lib().dctc_carver_resize_width(self._h, int(n_seams), _ptr(seams) if n_seams else None),
+               "dctc_carver_resize_width")
+        return seams
+
     def carve_and_update(self, seam_x, want_band=True):
         """Removes one vertical seam; returns (band_values, xmin, xmax) like liblqr's update_emap would visit."""
         w, h = self.carver_size()

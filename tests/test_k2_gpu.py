@@ -139,3 +139,45 @@ def test_gpu_retarget_height_and_energy_image(ctx):
     e = en / (1.0 + en)
     want = np.floor(255.0 * (e - e.min()) / (e.max() - e.min()) + 0.5).astype(np.uint8)
     assert np.abs(got["energy_image"].astype(int) - want.astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("b,ch,w,h,n", [(8, 3, 150, 90, 25), (8, 1, 97, 75, 40), (4, 3, 64, 33, 10), (16, 3, 130, 70, 12),
+                                        (8, 3, 1100, 40, 30), (8, 3, 40, 300, 8), (2, 1, 9, 1, 3)])
+def test_device_seam_loop_equals_host_carver(ctx, b, ch, w, h, n):
+    """dctc_carver_resize_width (seam DP + back-track + carve + band update, all on the device) must remove exactly
+    the seams the host carver (liblqr stand-in, incremental cumulative map on the CPU) removes: same tie rules
+    (first strict minimum among the parents, leftmost minimum of the last row), same FP32 sums."""
+    from dct_carver_b200 import host
+    img = ol.synth_image(w, h, ch, 500 + w, 0)
+    ctx.set_params(b, 0.5, 0.5)
+    want = host.render(img, -n, b, 0.5, 0.5, ctx=ctx)
+    ctx.set_params(b, 0.5, 0.5)
+    ctx.carver_load(img)
+    seams = ctx.carver_resize_width(n)
+    assert np.array_equal(seams, want["seams"])
+    assert ctx.carver_size() == (w - n, h)
+    got_img = ctx.carver_image()
+    assert np.array_equal(got_img.reshape(want["image"].shape), want["image"])
+    # the resident energy plane is the full map of the carved image
+    assert np.array_equal(ctx.carver_energy(), ctx.energy_full(want["image"]))
+
+
+def test_device_seam_loop_ties_and_flat_image(ctx):
+    """Constant image: every energy is 0, every cumulative value ties; liblqr's rule then removes column 0 in every
+    row, every time (leftmost minimum, first strict minimum among parents)."""
+    img = np.full((20, 30, 3), 77, np.uint8)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.carver_load(img)
+    seams = ctx.carver_resize_width(5)
+    assert (seams == 0).all()
+    assert ctx.carver_size() == (25, 20)
+
+
+def test_device_seam_loop_state_errors(ctx):
+    img = ol.synth_image(16, 8, 3, 3, 0)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.carver_load(img)
+    with pytest.raises(dc.DctcError) as e:
+        ctx.carver_resize_width(16)
+    assert e.value.status == dc.ERR_STATE
+    assert ctx.carver_resize_width(0).shape == (0, 8)

@@ -25,11 +25,26 @@ def main():
     t0 = time.perf_counter()
     r = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx)
     dt = time.perf_counter() - t0
+    lh = ctx.launches - l0
+    # the same retarget with the whole seam loop on the device (dctc_carver_resize_width)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.carver_load(img[:256, :256])
+    ctx.carver_resize_width(8)          # warm-up
+    l1 = ctx.launches
+    t1 = time.perf_counter()
+    ctx.carver_load(img)
+    t_load = time.perf_counter() - t1
+    seams = ctx.carver_resize_width(n)
+    dt_dev = time.perf_counter() - t1
+    same = bool((seams == r["seams"]).all())
     print(json.dumps({
         "workload": "1920x1080 RGB -> %dx1080, %d vertical seams, blocksize 8" % (w - n, n),
+        "device_loop_total_s": dt_dev, "device_loop_us_per_seam": 1e6 * (dt_dev - t_load) / n,
+        "device_loop_load_and_full_map_s": t_load, "device_loop_gpu_launches": ctx.launches - l1,
+        "device_loop_seams_equal_host_loop": same,
         "total_s": dt, "us_per_seam": 1e6 * dt / n, "seams_per_s": n / dt,
         "energy_s (K1 full + K2 band incl. H2D/D2H)": r["t_energy"], "cumulative_map_s (host)": r["t_mmap"],
-        "seam_search_carve_s (host)": r["t_seam"], "gpu_launches": ctx.launches - l0,
+        "seam_search_carve_s (host)": r["t_seam"], "gpu_launches": lh,
         "us_per_seam_energy": 1e6 * r["t_energy"] / n,
     }))
 

@@ -1,0 +1,8 @@
+import sys
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import dct_carver_b200 as dc, oracle_lib as ol
+img = ol.synth_image(1920, 1080, 3, 0xD0C7CA14, 0)
+ctx = dc.Context(0)
+ctx.set_params(8, 0.5, 0.5)
+ctx.carver_load(img)
+ctx.carver_resize_width(6)
