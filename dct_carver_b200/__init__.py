@@ -24,6 +24,7 @@ ABI_SYMBOLS = [
     "dctc_energy_full", "dctc_energy_full_dev", "dctc_energy_batch_dev", "dctc_energy_band_dev", "dctc_energy_batch",
     "dctc_carver_load", "dctc_carver_width", "dctc_carver_height", "dctc_carver_energy", "dctc_carve_and_update",
     "dctc_carver_image", "dctc_carver_resize_width", "dctc_pixel_energy",
+    "dctc_energy_minmax_dev", "dctc_energy_image_dev", "dctc_carver_energy_image",
     "dctc_synth_fill_dev", "dctc_synth_byte", "dctc_ipc_export", "dctc_ipc_open", "dctc_ipc_close",
     "dctc_dev_alloc", "dctc_dev_free", "dctc_host_alloc_pinned", "dctc_host_free_pinned", "dctc_memcpy_h2d",
     "dctc_memcpy_d2h", "dctc_memset_dev", "dctc_sync", "dctc_timer_begin", "dctc_timer_end",
@@ -87,6 +88,9 @@ def lib():
         "dctc_carve_and_update": (i32, [vp, vp, vp, vp, vp]),
         "dctc_carver_image": (i32, [vp, vp]),
         "dctc_carver_resize_width": (i32, [vp, i32, vp]),
+        "dctc_energy_minmax_dev": (i32, [vp, vp, C.c_size_t, i32, i32, vp]),
+        "dctc_energy_image_dev": (i32, [vp, vp, C.c_size_t, i32, i32, vp, vp, C.c_size_t, i32]),
+        "dctc_carver_energy_image": (i32, [vp, vp]),
         "dctc_pixel_energy": (f32, [i32, i32, i32, i32, vp, vp]),
         "dctc_synth_fill_dev": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, u32, i32, i32, i32]),
         "dctc_synth_byte": (C.c_uint8, [u32, u32, u32, u32, u32, i32]),
@@ -288,6 +292,26 @@ class Context:
         _check(lib().dctc_carver_resize_width(self._h, int(n_seams), _ptr(seams) if n_seams else None),
                "dctc_carver_resize_width")
         return seams
+
+    def carver_energy_image(self):
+        """8-bit grey energy image of the session's current map (liblqr get_energy_image semantics)."""
+        w, h = self.carver_size()
+        out = np.empty((h, w), np.uint8)
+        _check(lib().dctc_carver_energy_image(self._h, _ptr(out)), "dctc_carver_energy_image")
+        return out
+
+    def energy_minmax_dev(self, d_en, en_pitch, w, h):
+        lo_hi = np.empty(2, np.float32)
+        _check(lib().dctc_energy_minmax_dev(self._h, C.c_void_p(d_en), en_pitch, w, h, _ptr(lo_hi)), "dctc_energy_minmax_dev")
+        return lo_hi
+
+    def energy_image_dev(self, d_en, en_pitch, w, h, d_out, out_pitch, lo_hi=None, sync=True):
+        p = None
+        if lo_hi is not None:
+            lo_hi = np.ascontiguousarray(lo_hi, dtype=np.float32)
+            p = _ptr(lo_hi)
+        _check(lib().dctc_energy_image_dev(self._h, C.c_void_p(d_en), en_pitch, w, h, p, C.c_void_p(d_out), out_pitch,
+                                           int(sync)), "dctc_energy_image_dev")
 
     def carve_and_update(self, seam_x, want_band=True):
         """Removes one vertical seam; returns (band_values, xmin, xmax) like liblqr's update_emap would visit."""

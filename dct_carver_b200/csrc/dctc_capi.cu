@@ -107,6 +107,8 @@ void dctc_destroy(dctc_context* ctx)
         if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     }
     if (ctx->tc_counters) cudaFree(ctx->tc_counters);
+    if (ctx->k3_lohi) cudaFree(ctx->k3_lohi);
+    if (ctx->k3_img) cudaFree(ctx->k3_img);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

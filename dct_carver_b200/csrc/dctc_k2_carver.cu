@@ -137,40 +137,75 @@ __global__ void __launch_bounds__(DP_NT) dctc_seam_dp_kernel(const float* __rest
     }
     for (int y = 1; y < ring; y++) stage(y);
     __syncthreads();
-    for (int y = 1; y < h; y++) {
-        stage(y + ring - 1);
-        switch (ring) {   // all but the newest ring-1 groups have landed: row y is in shared memory
-        case 8: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        }
-        const float* erow = enr + (size_t) (y & (ring - 1)) * W4;
-        int8_t* drow = dir + (size_t) y * dir_pitch;
+#ifdef DCTC_SYNC_DEBUG
+    const long long dbg_t0 = clock64();
+#endif
+    // Main chain, kept to a few dozen instructions per row (the single SM is issue-bound): all addresses are running
+    // pointers, the staging ring wraps by pointer comparison, only the thread that owns the row tail patches it.
+    {
+        const int x0 = 4 * tid;                                   // DP_P == 1 fast path uses group 0 only; others loop below
+        const bool tail = x0 < W4 && x0 + 4 > w;
+        const uint32_t ring_bytes = (uint32_t) ring * (uint32_t) W4 * 4u;
+        const uint32_t enr_s = (uint32_t) __cvta_generic_to_shared(enr);
+        uint32_t st_dst = enr_s + (uint32_t) ((ring & (ring - 1)) == 0 ? ((ring) & (ring - 1)) : 0) * 0u;   // row (ring) & (ring-1) == 0
+        st_dst = enr_s + (uint32_t) x0 * 4u;                      // next row to stage is y = ring -> slot 0
+        uint32_t ld_off = (uint32_t) W4 * 4u;                     // row 1 -> slot 1 (byte offset inside the ring)
+        if (ring == 1) ld_off = 0;
+        const float* st_src = en + (size_t) ring * en_pitch + x0; // source of the next row to stage
+        int st_rows = h - ring;                                    // rows still to be staged
+        int8_t* drow = dir + dir_pitch + x0;
+        for (int y = 1; y < h; y++) {
 #pragma unroll
-        for (int p = 0; p < DP_P; p++) {
-            const int x0 = 4 * (tid + p * DP_NT);
-            if (x0 < W4) {
-                const float l = prev[x0 + 3], r = prev[x0 + 8];
-                const float4 m = *reinterpret_cast<const float4*>(prev + x0 + 4);
-                const float4 e = *reinterpret_cast<const float4*>(erow + x0);
-                int d0, d1, d2, d3;
-                float4 o;
-                o.x = dp_cell(l, m.x, m.y, e.x, d0);
-                o.y = dp_cell(m.x, m.y, m.z, e.y, d1);
-                o.z = dp_cell(m.y, m.z, m.w, e.z, d2);
-                o.w = dp_cell(m.z, m.w, r, e.w, d3);
-                if (x0 + 4 > w) {   // tail group: cells right of the image stay +inf
-                    if (x0 + 1 >= w) o.y = INF;
-                    if (x0 + 2 >= w) o.z = INF;
-                    if (x0 + 3 >= w) o.w = INF;
-                }
-                *reinterpret_cast<float4*>(next + x0 + 4) = o;
-                *reinterpret_cast<uint32_t*>(drow + x0) = (uint32_t) (d0 & 255) | ((uint32_t) (d1 & 255) << 8) | ((uint32_t) (d2 & 255) << 16) | ((uint32_t) (d3 & 255) << 24);
+            for (int p = 0; p < DP_P; p++) {
+                const int xo = 4 * p * DP_NT;
+                if (st_rows > 0 && x0 + xo < W4)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_dst + (uint32_t) xo * 4u), "l"(st_src + xo) : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            st_rows--;
+            st_src += en_pitch;
+            st_dst += (uint32_t) W4 * 4u;
+            if (st_dst >= enr_s + ring_bytes + (uint32_t) x0 * 4u) st_dst -= ring_bytes;
+            switch (ring) {   // all but the newest ring-1 groups have landed: row y is in shared memory
+            case 8: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+            case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+            default: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+            }
+            const float* erow = reinterpret_cast<const float*>(reinterpret_cast<const char*>(enr) + ld_off);
+#pragma unroll
+            for (int p = 0; p < DP_P; p++) {
+                const int xp = x0 + 4 * p * DP_NT;
+                if (xp < W4) {
+                    const float l = prev[xp + 3], r = prev[xp + 8];
+                    const float4 m = *reinterpret_cast<const float4*>(prev + xp + 4);
+                    const float4 e = *reinterpret_cast<const float4*>(erow + xp);
+                    int d0, d1, d2, d3;
+                    float4 o;
+                    o.x = dp_cell(l, m.x, m.y, e.x, d0);
+                    o.y = dp_cell(m.x, m.y, m.z, e.y, d1);
+                    o.z = dp_cell(m.y, m.z, m.w, e.z, d2);
+                    o.w = dp_cell(m.z, m.w, r, e.w, d3);
+                    if (xp + 4 > w) {   // tail group: cells right of the image stay +inf
+                        if (xp + 1 >= w) o.y = INF;
+                        if (xp + 2 >= w) o.z = INF;
+                        if (xp + 3 >= w) o.w = INF;
+                    }
+                    *reinterpret_cast<float4*>(next + xp + 4) = o;
+                    *reinterpret_cast<uint32_t*>(drow + 4 * p * DP_NT) =
+                        (uint32_t) (d0 & 255) | ((uint32_t) (d1 & 255) << 8) | ((uint32_t) (d2 & 255) << 16) | ((uint32_t) (d3 & 255) << 24);
+                }
+            }
+            (void) tail;
+            drow += dir_pitch;
+            ld_off += (uint32_t) W4 * 4u;
+            if (ld_off >= ring_bytes) ld_off = 0;
+            __syncthreads();
+            float* t = prev; prev = next; next = t;
         }
-        __syncthreads();
-        float* t = prev; prev = next; next = t;
     }
+#ifdef DCTC_SYNC_DEBUG
+    const long long dbg_t1 = clock64();
+#endif
     // leftmost minimum of the last row
     const float* last = prev;
     float bv = INF;
@@ -226,6 +261,9 @@ __global__ void __launch_bounds__(DP_NT) dctc_seam_dp_kernel(const float* __rest
             }
             __syncwarp();
         }
+#ifdef DCTC_SYNC_DEBUG
+        if (tid == 0) printf("dp kernel w %d h %d: chain %lld clk, reduce+backtrack %lld clk\n", w, h, dbg_t1 - dbg_t0, clock64() - dbg_t1);
+#endif
     }
 }
 

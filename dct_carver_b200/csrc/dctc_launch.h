@@ -52,6 +52,10 @@ struct dctc_context {
     int c_w0 = 0, c_w = 0, c_h = 0, c_ch = 0;
     size_t c_pitch = 0;
     bool mirror_valid = false;
+    // K3 energy-image export
+    unsigned int* k3_lohi = nullptr;   // device (min, max) of the compressed energies, as float bit patterns
+    uint8_t* k3_img = nullptr;
+    size_t k3_img_cap = 0;
 };
 
 int dctc_fail_cuda(dctc_context* ctx, cudaError_t e);

@@ -398,8 +398,13 @@ int dctc_lqr_carver_get_energy(DctcLqrCarver *r, float *buffer)
 int dctc_lqr_carver_get_energy_image(DctcLqrCarver *r, uint8_t *buffer)
 {
     size_t i, n = (size_t) r->w * r->h;
-    float lo, hi, *e = (float *) malloc(sizeof(float) * n);
+    float lo, hi, *e;
     int rc;
+    if (r->gpu) {   /* K3: compression, min/max and quantisation on the device, same FP32 operation order */
+        if (dctc_carver_load(r->gpu, r->rgb, r->w, r->h, r->ch, (size_t) r->pitch * r->ch) != DCTC_OK) return DCTC_LQR_ERROR;
+        return dctc_carver_energy_image(r->gpu, buffer) == DCTC_OK ? DCTC_LQR_OK : DCTC_LQR_ERROR;
+    }
+    e = (float *) malloc(sizeof(float) * n);
     if (!e) return DCTC_LQR_NOMEM;
     rc = dctc_lqr_carver_get_energy(r, e);
     if (rc) { free(e); return rc; }

@@ -143,6 +143,21 @@ int dctc_carver_image(dctc_context *ctx, uint8_t *out);
  * delta_x = 1, rigidity = 0 (src/render.c:313). */
 int dctc_carver_resize_width(dctc_context *ctx, int n_seams, int *seams_out);
 
+/* ---- K3: energy-image export ------------------------------------------------------------------------------
+ * Replaces lqr_carver_get_energy_image(carver, buf, orientation, LQR_COLDEPTH_8I, LQR_GREY_IMAGE) as called at
+ * src/render.c:191 (the plug-in's "output energy" option, src/render.c:175-202): e -> e/(1+e), min-max normalise,
+ * 8-bit grey. */
+
+/* (min, max) of e/(1+e) over a device-resident w*h float plane; lo_hi receives two floats.  For a map sharded into
+ * row bands each rank calls this on its band and the pairs are all-reduced (min, max) before dctc_energy_image_dev. */
+int dctc_energy_minmax_dev(dctc_context *ctx, const float *d_en, size_t en_pitch, int w, int h, float *lo_hi);
+/* Writes the 8-bit grey energy image of a device-resident plane.  lo_hi = the pair to normalise with (e.g. the
+ * all-reduced one), or NULL to compute it from this plane on the device. */
+int dctc_energy_image_dev(dctc_context *ctx, const float *d_en, size_t en_pitch, int w, int h, const float *lo_hi,
+                          uint8_t *d_out, size_t out_pitch, int sync);
+/* Energy image of the carver session's current map, copied to the host (w*h bytes, pitch w). */
+int dctc_carver_energy_image(dctc_context *ctx, uint8_t *out);
+
 /* ---- per-pixel symbol, kept for ABI parity ---------------------------------------------------------------
  * Same signature as the reference's LqrEnergyFunc dct_pixel_energy (src/render.c:134).  `extra_data` must
  * point to a DctcCarverEnergyParams.  A per-pixel call cannot be GPU-backed, so it is served from the host

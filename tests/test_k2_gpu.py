@@ -181,3 +181,33 @@ def test_device_seam_loop_state_errors(ctx):
         ctx.carver_resize_width(16)
     assert e.value.status == dc.ERR_STATE
     assert ctx.carver_resize_width(0).shape == (0, 8)
+
+
+@pytest.mark.parametrize("ch,w,h", [(3, 130, 77), (1, 64, 33), (3, 1, 1)])
+def test_energy_image_export_equals_host_formula(ctx, ch, w, h):
+    """K3 (lqr_carver_get_energy_image semantics, src/render.c:191): e/(1+e), min-max, 8-bit — byte-identical to the
+    host formula evaluated in FP32 on the same energies, also when (lo, hi) are supplied from outside (band sharding)."""
+    img = ol.synth_image(w, h, ch, 31, 3)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.carver_load(img)
+    en = ctx.carver_energy()
+    c = en / (np.float32(1.0) + en)
+    lo, hi = c.min(), c.max()
+    if hi > lo:
+        want = ((np.float32(255.0) * (c - lo)) / (hi - lo) + np.float32(0.5)).astype(np.uint8)
+    else:
+        want = np.zeros((h, w), np.uint8)
+    got = ctx.carver_energy_image()
+    assert np.array_equal(got, want)
+    # two-pass form used by the row-band sharding: min/max first, then scale with the (all-reduced) pair
+    d_en = ctx.dev_alloc(en.nbytes)
+    d_out = ctx.dev_alloc(w * h)
+    ctx.h2d(d_en, en)
+    lo_hi = ctx.energy_minmax_dev(d_en, w, w, h)
+    assert lo_hi[0] == lo and lo_hi[1] == hi
+    ctx.energy_image_dev(d_en, w, w, h, d_out, w, lo_hi=lo_hi)
+    out = np.empty((h, w), np.uint8)
+    ctx.d2h(out, d_out)
+    assert np.array_equal(out, want)
+    ctx.dev_free(d_en)
+    ctx.dev_free(d_out)

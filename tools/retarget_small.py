@@ -1,6 +1,8 @@
 import sys
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import os
 import dct_carver_b200 as dc, oracle_lib as ol
+if os.environ.get("DCTC_LIB"): dc.LIB_PATH = os.environ["DCTC_LIB"]
 img = ol.synth_image(1920, 1080, 3, 0xD0C7CA14, 0)
 ctx = dc.Context(0)
 ctx.set_params(8, 0.5, 0.5)
