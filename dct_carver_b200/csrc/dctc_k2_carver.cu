@@ -69,157 +69,123 @@ __global__ void __launch_bounds__(NT) dctc_carve_rows_kernel(uint8_t* __restrict
 // dct_carver_b200/host/dctc_lqr.c and oracle/oracle_carver.c):
 //   m[0][x] = en[0][x];  m[y][x] = en[y][x] + min(m[y-1][x-1], m[y-1][x], m[y-1][x+1])   (FP32, range clipped)
 //   parent of (y, x) = FIRST strict minimum scanning x-1, x, x+1;  seam end = LEFTMOST minimum of the last row.
-// The map is rebuilt from scratch for every seam (same values as liblqr's incremental update_mmap).  One CTA: row y
-// depends on the whole row y-1, so the rows are a chain of h barrier-separated steps; the previous row lives in
-// shared memory (guarded by +inf at both ends, which reproduces the clipping), the parent offsets (-1/0/+1) go to a
-// byte plane in global memory for the back-track, which warp 0 runs afterwards in batches of 32 rows: the path
-// moves at most one column per row, so the 32 rows' 72-byte windows around the current column are fetched with
-// independent loads (one L2 round trip per batch instead of one per row).
+// The map is rebuilt from scratch for every seam (same values as liblqr's incremental update_mmap).  Row y depends on
+// the whole row y-1, so the rows are a chain of h barrier-separated steps on ONE SM.  A first version that kept the
+// rows in shared memory was bound by shared-memory bandwidth (measured ~600 clk per 1920-px row); here every thread
+// keeps its four adjacent cells of the previous row in REGISTERS, gets the two neighbouring cells with warp
+// shuffles (warp-edge lanes through a 2-float-per-warp shared exchange), prefetches the energies two rows ahead
+// with 128-bit global loads and writes the cumulative rows to a global float plane.  The parent choice is not
+// recorded: warp 0 re-derives it during the back-track from that plane, in batches of 32 rows -- the path moves at
+// most one column per row, so the 32 rows' 80-float windows around the current column are fetched with independent
+// coalesced loads (one L2 round trip per batch).  Cells right of the image hold +inf, which is the range clipping.
+#ifndef DP_EXP
+#define DP_EXP 0   // timing experiments only
+#endif
 constexpr int DP_NT = 512;        // threads of the single DP CTA; every thread owns groups of 4 adjacent columns
 constexpr int DP_MAXP = 4;        // groups per thread: widths up to 4 * 512 * 4 = 8192
+constexpr int DP_WIN = 80;        // back-track window (floats)
 
-// first strict minimum among (a, b, c) scanned in that order: value and parent offset -1 / 0 / +1
-__device__ __forceinline__ float dp_cell(float a, float b, float c, float e, int& d)
-{
-    const float t = fminf(a, b);
-    d = (b < a) ? 0 : -1;
-    d = (c < t) ? 1 : d;
-    return e + fminf(t, c);
-}
-
-// The whole kernel runs on ONE SM, so it is bound by instruction issue: four adjacent columns per thread (one 128-bit
-// shared load of the previous row + two scalar halo loads, one 128-bit store, one packed 4-byte store of the parent
-// offsets), energies staged through a cp.async ring a few rows ahead.  Cell x of a row lives at index x + 4; the four
-// floats in front and behind hold +inf, which reproduces the range clipping at the image borders.
 template <int DP_P>               // column groups per thread of this instantiation (1, 2 or 4)
 __global__ void __launch_bounds__(DP_NT) dctc_seam_dp_kernel(const float* __restrict__ en, size_t en_pitch, int w, int h,
-                                                             int8_t* __restrict__ dir, size_t dir_pitch,
-                                                             int* __restrict__ seam, int* __restrict__ seam_log, int ring)
+                                                             float* __restrict__ mplane, size_t m_pitch,
+                                                             int* __restrict__ seam, int* __restrict__ seam_log)
 {
-    extern __shared__ __align__(16) float dp_sm[];
+    constexpr int NW = DP_NT / 32;
+    __shared__ float edge_l[2][DP_P][NW], edge_r[2][DP_P][NW];   // first / last cell of every warp's span, double buffered
+    __shared__ float red_v[NW];
+    __shared__ int red_i[NW];
+    __shared__ __align__(16) float win[32][DP_WIN];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = 4 * tid;
     const int W4 = (w + 3) & ~3;
-    const int RB = W4 + 8;
-    float* prev = dp_sm;
-    float* next = dp_sm + RB;
-    float* enr = dp_sm + 2 * RB;                     // `ring` staged energy rows of W4 floats (ring is a power of two)
-    __shared__ float red_v[DP_NT / 32];
-    __shared__ int red_i[DP_NT / 32];
-    __shared__ int win[32][18];
-    const int tid = threadIdx.x;
     const float INF = __int_as_float(0x7f800000);
-    if (tid < 4) { prev[tid] = INF; next[tid] = INF; prev[W4 + 4 + tid] = INF; next[W4 + 4 + tid] = INF; }
-    // Every thread copies and later reads only its own columns: cp.async.wait_group alone orders the staged rows.
-    auto stage = [&](int y) {
-        if (y < h) {
-            float* dst = enr + (size_t) (y & (ring - 1)) * W4;
-            const float* src = en + (size_t) y * en_pitch;
-#pragma unroll
-            for (int p = 0; p < DP_P; p++) {
-                const int x0 = 4 * (tid + p * DP_NT);
-                if (x0 < W4) {
-                    const uint32_t d32 = (uint32_t) __cvta_generic_to_shared(dst + x0);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src + x0) : "memory");
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    auto load_row = [&](int y, int p) -> float4 {
+        const int xp = x0 + 4 * p * DP_NT;
+        return (y < h && xp < W4) ? __ldg(reinterpret_cast<const float4*>(en + (size_t) y * en_pitch + xp)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    auto patch_tail = [&](float4& v, int xp) {
+        if (xp >= w) v.x = INF;
+        if (xp + 1 >= w) v.y = INF;
+        if (xp + 2 >= w) v.z = INF;
+        if (xp + 3 >= w) v.w = INF;
+    };
+    constexpr int PF = 8;                 // energy rows in flight per thread (registers): covers the L2 latency of a lone SM
+    float4 cur[DP_P], e[PF][DP_P];
 #pragma unroll
     for (int p = 0; p < DP_P; p++) {
-        const int x0 = 4 * (tid + p * DP_NT);
-        if (x0 < W4) {
-            float4 v = *reinterpret_cast<const float4*>(en + x0);
-            if (x0 + 1 >= w) v.y = INF;
-            if (x0 + 2 >= w) v.z = INF;
-            if (x0 + 3 >= w) v.w = INF;
-            *reinterpret_cast<float4*>(prev + x0 + 4) = v;
-        }
+        const int xp = x0 + 4 * p * DP_NT;
+        cur[p] = load_row(0, p);
+        if (xp < W4) *reinterpret_cast<float4*>(mplane + xp) = cur[p];
+        patch_tail(cur[p], xp);
+#pragma unroll
+        for (int k = 0; k < PF; k++) e[k][p] = load_row(1 + k, p);     // e[k] holds row y with (y - 1) % PF == k
+        if (lane == 0) edge_l[0][p][warp] = cur[p].x;
+        if (lane == 31) edge_r[0][p][warp] = cur[p].w;
     }
-    for (int y = 1; y < ring; y++) stage(y);
     __syncthreads();
 #ifdef DCTC_SYNC_DEBUG
     const long long dbg_t0 = clock64();
 #endif
-    // Main chain, kept to a few dozen instructions per row (the single SM is issue-bound): all addresses are running
-    // pointers, the staging ring wraps by pointer comparison, only the thread that owns the row tail patches it.
-    {
-        const int x0 = 4 * tid;                                   // DP_P == 1 fast path uses group 0 only; others loop below
-        const bool tail = x0 < W4 && x0 + 4 > w;
-        const uint32_t ring_bytes = (uint32_t) ring * (uint32_t) W4 * 4u;
-        const uint32_t enr_s = (uint32_t) __cvta_generic_to_shared(enr);
-        uint32_t st_dst = enr_s + (uint32_t) ((ring & (ring - 1)) == 0 ? ((ring) & (ring - 1)) : 0) * 0u;   // row (ring) & (ring-1) == 0
-        st_dst = enr_s + (uint32_t) x0 * 4u;                      // next row to stage is y = ring -> slot 0
-        uint32_t ld_off = (uint32_t) W4 * 4u;                     // row 1 -> slot 1 (byte offset inside the ring)
-        if (ring == 1) ld_off = 0;
-        const float* st_src = en + (size_t) ring * en_pitch + x0; // source of the next row to stage
-        int st_rows = h - ring;                                    // rows still to be staged
-        int8_t* drow = dir + dir_pitch + x0;
-        for (int y = 1; y < h; y++) {
+    float* mrow = mplane + m_pitch + x0;
+    for (int yb = 1; yb < h; yb += PF) {
 #pragma unroll
-            for (int p = 0; p < DP_P; p++) {
-                const int xo = 4 * p * DP_NT;
-                if (st_rows > 0 && x0 + xo < W4)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_dst + (uint32_t) xo * 4u), "l"(st_src + xo) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            st_rows--;
-            st_src += en_pitch;
-            st_dst += (uint32_t) W4 * 4u;
-            if (st_dst >= enr_s + ring_bytes + (uint32_t) x0 * 4u) st_dst -= ring_bytes;
-            switch (ring) {   // all but the newest ring-1 groups have landed: row y is in shared memory
-            case 8: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-            case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-            default: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-            }
-            const float* erow = reinterpret_cast<const float*>(reinterpret_cast<const char*>(enr) + ld_off);
+        for (int k = 0; k < PF; k++) {
+            const int y = yb + k;
+            if (y < h) {                                                    // uniform across the CTA
+                const int rb = (y - 1) & 1, wb = y & 1;
 #pragma unroll
-            for (int p = 0; p < DP_P; p++) {
-                const int xp = x0 + 4 * p * DP_NT;
-                if (xp < W4) {
-                    const float l = prev[xp + 3], r = prev[xp + 8];
-                    const float4 m = *reinterpret_cast<const float4*>(prev + xp + 4);
-                    const float4 e = *reinterpret_cast<const float4*>(erow + xp);
-                    int d0, d1, d2, d3;
+                for (int p = 0; p < DP_P; p++) {
+                    const int xp = x0 + 4 * p * DP_NT;
+                    const float4 ee = e[k][p];
+#if !(DP_EXP & 1)
+                    e[k][p] = load_row(y + PF, p);                          // PF rows ahead: off the chain
+#endif
+                    float l = __shfl_up_sync(0xffffffffu, cur[p].w, 1);
+                    float r = __shfl_down_sync(0xffffffffu, cur[p].x, 1);
+                    // warp-edge lanes take their neighbour from the shared exchange; every lane issues the (broadcast)
+                    // loads so that the row chain stays free of divergent branches
+                    const bool has_l = warp > 0 || p > 0, has_r = warp < NW - 1 || p < DP_P - 1;
+                    const float el = edge_r[rb][warp > 0 ? p : (p > 0 ? p - 1 : 0)][warp > 0 ? warp - 1 : NW - 1];
+                    const float er = edge_l[rb][warp < NW - 1 ? p : (p < DP_P - 1 ? p + 1 : p)][warp < NW - 1 ? warp + 1 : 0];
+                    l = lane == 0 ? (has_l ? el : INF) : l;
+                    r = lane == 31 ? (has_r ? er : INF) : r;
                     float4 o;
-                    o.x = dp_cell(l, m.x, m.y, e.x, d0);
-                    o.y = dp_cell(m.x, m.y, m.z, e.y, d1);
-                    o.z = dp_cell(m.y, m.z, m.w, e.z, d2);
-                    o.w = dp_cell(m.z, m.w, r, e.w, d3);
-                    if (xp + 4 > w) {   // tail group: cells right of the image stay +inf
-                        if (xp + 1 >= w) o.y = INF;
-                        if (xp + 2 >= w) o.z = INF;
-                        if (xp + 3 >= w) o.w = INF;
-                    }
-                    *reinterpret_cast<float4*>(next + xp + 4) = o;
-                    *reinterpret_cast<uint32_t*>(drow + 4 * p * DP_NT) =
-                        (uint32_t) (d0 & 255) | ((uint32_t) (d1 & 255) << 8) | ((uint32_t) (d2 & 255) << 16) | ((uint32_t) (d3 & 255) << 24);
+                    o.x = ee.x + fminf(fminf(l, cur[p].x), cur[p].y);
+                    o.y = ee.y + fminf(fminf(cur[p].x, cur[p].y), cur[p].z);
+                    o.z = ee.z + fminf(fminf(cur[p].y, cur[p].z), cur[p].w);
+                    o.w = ee.w + fminf(fminf(cur[p].z, cur[p].w), r);
+#if DP_EXP & 2
+                    if (o.x == 12345.678f)
+#endif
+                    if (xp < W4) *reinterpret_cast<float4*>(mrow + 4 * p * DP_NT) = o;
+                    if (xp + 4 > w) patch_tail(o, xp);                      // cells right of the image stay +inf
+                    cur[p] = o;
+                    if (lane == 0) edge_l[wb][p][warp] = o.x;
+                    if (lane == 31) edge_r[wb][p][warp] = o.w;
                 }
+                mrow += m_pitch;
+#if DP_EXP & 4
+                __syncwarp();
+#else
+                __syncthreads();
+#endif
             }
-            (void) tail;
-            drow += dir_pitch;
-            ld_off += (uint32_t) W4 * 4u;
-            if (ld_off >= ring_bytes) ld_off = 0;
-            __syncthreads();
-            float* t = prev; prev = next; next = t;
         }
     }
 #ifdef DCTC_SYNC_DEBUG
     const long long dbg_t1 = clock64();
 #endif
     // leftmost minimum of the last row
-    const float* last = prev;
     float bv = INF;
     int bi = 0x7fffffff;
 #pragma unroll
     for (int p = 0; p < DP_P; p++) {
-        const int x0 = 4 * (tid + p * DP_NT);
+        const int xp = x0 + 4 * p * DP_NT;
+        const float c4[4] = {cur[p].x, cur[p].y, cur[p].z, cur[p].w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int x = x0 + k;
-            if (x < w) {
-                const float v = last[x + 4];
-                if (v < bv || bi == 0x7fffffff) { bv = v; bi = x; }   // ascending x per thread: strict < keeps the leftmost
-            }
+            const int x = xp + k;
+            if (x < w && (c4[k] < bv || bi == 0x7fffffff)) { bv = c4[k]; bi = x; }   // ascending x per thread: strict < keeps the leftmost
         }
     }
 #pragma unroll
@@ -228,12 +194,11 @@ __global__ void __launch_bounds__(DP_NT) dctc_seam_dp_kernel(const float* __rest
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
     }
-    if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
-    __threadfence_block();
-    __syncthreads();
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();   // also orders this CTA's global writes of the cumulative plane before warp 0 reads them back
     if (tid < 32) {
-        bv = tid < DP_NT / 32 ? red_v[tid] : INF;
-        bi = tid < DP_NT / 32 ? red_i[tid] : 0x7fffffff;
+        bv = tid < NW ? red_v[tid] : INF;
+        bi = tid < NW ? red_i[tid] : 0x7fffffff;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -241,28 +206,45 @@ __global__ void __launch_bounds__(DP_NT) dctc_seam_dp_kernel(const float* __rest
             if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
         }
         // back-track (warp 0; every lane follows the same path, lane 0 records it)
-        const int lane = tid;
         int x = bi;
         if (lane == 0) { seam[h - 1] = x; if (seam_log) seam_log[h - 1] = x; }
-        const int max_base = (int) dir_pitch - 72;
+        const int max_base = (int) m_pitch - DP_WIN;
         for (int ytop = h - 1; ytop >= 1; ytop -= 32) {
-            int base = (x - 32) & ~3;
+            // the parents of rows ytop, ytop-1, ... are chosen in rows ytop-1, ytop-2, ...: window row i = image row ytop-1-i
+            int base = (x - 36) & ~3;
             base = base < 0 ? 0 : (base > max_base ? max_base : base);
-            const int yy = ytop - lane;
-            if (yy >= 1) {
-                const int* src = reinterpret_cast<const int*>(dir + (size_t) yy * dir_pitch + base);
+            float4 t[32];
 #pragma unroll
-                for (int k = 0; k < 18; k++) win[lane][k] = __ldcg(src + k);
+            for (int i = 0; i < 32; i++) {
+                const int yy = ytop - 1 - i;
+                t[i] = (yy >= 0 && lane < DP_WIN / 4) ? __ldcg(reinterpret_cast<const float4*>(mplane + (size_t) yy * m_pitch + base) + lane)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (lane < DP_WIN / 4) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) reinterpret_cast<float4*>(win[i])[lane] = t[i];
             }
             __syncwarp();
-            for (int i = 0; i < 32 && ytop - i >= 1; i++) {
-                x += (int) reinterpret_cast<const int8_t*>(win[i])[x - base];
-                if (lane == 0) { seam[ytop - i - 1] = x; if (seam_log) seam_log[ytop - i - 1] = x; }
+            const int steps = ytop < 32 ? ytop : 32;
+            for (int i = 0; i < steps; i++) {
+                const float* wr = win[i] - base;
+                const float a = x > 0 ? wr[x - 1] : INF;
+                const float b = wr[x];
+                const float c = x < w - 1 ? wr[x + 1] : INF;
+                int arg = x - 1;
+                float best = a;
+                if (b < best) { best = b; arg = x; }
+                if (c < best) arg = x + 1;
+                x = arg;
+                if (lane == 0) { seam[ytop - 1 - i] = x; if (seam_log) seam_log[ytop - 1 - i] = x; }
             }
             __syncwarp();
         }
 #ifdef DCTC_SYNC_DEBUG
-        if (tid == 0) printf("dp kernel w %d h %d: chain %lld clk, reduce+backtrack %lld clk\n", w, h, dbg_t1 - dbg_t0, clock64() - dbg_t1);
+        if (tid == 0) {
+            unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            printf("dp kernel w %d h %d: chain %lld clk, reduce+backtrack %lld clk, globaltimer %llu ns\n", w, h, dbg_t1 - dbg_t0, clock64() - dbg_t1, gt);
+        }
 #endif
     }
 }
@@ -410,11 +392,11 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     const int h = ctx->c_h, r = ctx->blocksize / 2, bs = band_stride(ctx);
     if (ctx->c_w > 4 * DP_NT * DP_MAXP) return DCTC_ERR_UNSUPPORTED;   // wider than one CTA's columns: use the host seam loop
     CK(ctx, cudaSetDevice(ctx->device));
-    // parent-offset plane: one byte per pixel, rows padded so that the 72-byte back-track windows stay inside
-    const size_t dir_pitch = (((size_t) ctx->c_w0 + 3) & ~(size_t) 3) < 72 ? 72 : (((size_t) ctx->c_w0 + 3) & ~(size_t) 3);
-    if (!ctx->c_dir) {
-        CK(ctx, cudaMalloc((void**) &ctx->c_dir, dir_pitch * (size_t) h));
-        CK(ctx, cudaMemsetAsync(ctx->c_dir, 0, dir_pitch * (size_t) h, ctx->stream));
+    // cumulative-map plane, rows padded so that the 80-float back-track windows stay inside
+    const size_t m_pitch = ctx->c_en_pitch < (size_t) DP_WIN ? (size_t) DP_WIN : ctx->c_en_pitch;
+    if (!ctx->c_m) {
+        CK(ctx, cudaMalloc((void**) &ctx->c_m, sizeof(float) * m_pitch * (size_t) h));
+        CK(ctx, cudaMemsetAsync(ctx->c_m, 0, sizeof(float) * m_pitch * (size_t) h, ctx->stream));
     }
     if (ctx->c_seam_log_cap < (size_t) n_seams * h) {
         if (ctx->c_seam_log) cudaFree(ctx->c_seam_log);
@@ -422,19 +404,14 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         CK(ctx, cudaMalloc((void**) &ctx->c_seam_log, sizeof(int) * (size_t) n_seams * h));
         ctx->c_seam_log_cap = (size_t) n_seams * h;
     }
-    // staged energy rows: 8, 4 or 2 deep, whatever fits beside the two cumulative rows
     const size_t w4 = ((size_t) ctx->c_w + 3) & ~(size_t) 3;
-    const size_t row_bytes = sizeof(float) * w4;
-    const int ring = (8 * row_bytes <= 160 * 1024) ? 8 : (4 * row_bytes <= 160 * 1024) ? 4 : 2;
-    const size_t dp_smem = sizeof(float) * 2 * (w4 + 8) + (size_t) ring * row_bytes;
     const int groups = (int) ((w4 / 4 + DP_NT - 1) / DP_NT);
     auto dp = groups <= 1 ? dctc_seam_dp_kernel<1> : groups <= 2 ? dctc_seam_dp_kernel<2> : dctc_seam_dp_kernel<4>;
-    if (dp_smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dp_smem));
     for (int s = 0; s < n_seams; s++) {
         const int w_old = ctx->c_w;
         // build_mmap + build_vpath
-        dp<<<1, DP_NT, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_dir, dir_pitch,
-                                                                ctx->c_seam, ctx->c_seam_log + (size_t) s * h, ring);
+        dp<<<1, DP_NT, 0, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam,
+                                         ctx->c_seam_log + (size_t) s * h);
 #ifdef DCTC_SYNC_DEBUG
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }
 #endif

@@ -40,8 +40,8 @@ struct dctc_context {
     uint8_t* c_img = nullptr;      // device image, pitch c_pitch, compacted in place per seam
     float* c_en = nullptr;         // device energy, pitch c_en_pitch floats (multiple of 4: 16-byte aligned rows)
     size_t c_en_pitch = 0;
-    float* c_m = nullptr;          // (unused: the seam DP keeps its rows in shared memory)
-    int8_t* c_dir = nullptr;       // parent offsets (-1/0/+1) of the seam DP, one byte per pixel
+    float* c_m = nullptr;          // cumulative map of the device seam DP (rebuilt per seam, read back by the back-track)
+    int8_t* c_dir = nullptr;       // (unused)
     int* c_seam_log = nullptr;     // seams of dctc_carver_resize_width, n_seams * h
     size_t c_seam_log_cap = 0;
     int* c_seam = nullptr;         // h entries
