@@ -259,8 +259,9 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_kind": "of " + peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel": "dctc_k1 (full energy map)",
-                "note": "blocksize 8 needs ~380 FP32 flop/px: CUDA-core variants are FMA-pipe bound, see DESIGN.md"}
+                "kernel": "dctc_k1_tc8_kernel (tcgen05 y-pass)" if (args.blocksize == 8 and args.kernel in (0, 3)) else "dctc_k1 (FP32)",
+                "note": "traffic = DRAM bytes per launch from ncu (profiles/traffic.json); blocksize 8 is compute-bound "
+                        "(24 tcgen05 MMAs + 32 FMNMX3 per 8x128 px), not HBM-bound: see DESIGN.md section 4"}
 
     # e2e: the same metric through the host-buffer C-ABI call, pinned host memory, copies inside the timed region
     e2e = None
