@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "dctc_energy_full", "dctc_energy_full_dev", "dctc_energy_batch_dev", "dctc_energy_band_dev", "dctc_energy_batch",
     "dctc_carver_load", "dctc_carver_width", "dctc_carver_height", "dctc_carver_energy", "dctc_carve_and_update",
     "dctc_carver_image", "dctc_carver_resize_width", "dctc_pixel_energy",
-    "dctc_energy_minmax_dev", "dctc_energy_image_dev", "dctc_carver_energy_image",
+    "dctc_energy_minmax_dev", "dctc_energy_image_dev", "dctc_carver_energy_image", "dctc_preview_energy",
     "dctc_synth_fill_dev", "dctc_synth_byte", "dctc_ipc_export", "dctc_ipc_open", "dctc_ipc_close",
     "dctc_dev_alloc", "dctc_dev_free", "dctc_host_alloc_pinned", "dctc_host_free_pinned", "dctc_memcpy_h2d",
     "dctc_memcpy_d2h", "dctc_memset_dev", "dctc_sync", "dctc_timer_begin", "dctc_timer_end",
@@ -91,6 +91,7 @@ def lib():
         "dctc_energy_minmax_dev": (i32, [vp, vp, C.c_size_t, i32, i32, vp]),
         "dctc_energy_image_dev": (i32, [vp, vp, C.c_size_t, i32, i32, vp, vp, C.c_size_t, i32]),
         "dctc_carver_energy_image": (i32, [vp, vp]),
+        "dctc_preview_energy": (i32, [vp, vp, i32, i32, i32, C.c_size_t, vp, vp]),
         "dctc_pixel_energy": (f32, [i32, i32, i32, i32, vp, vp]),
         "dctc_synth_fill_dev": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, u32, i32, i32, i32]),
         "dctc_synth_byte": (C.c_uint8, [u32, u32, u32, u32, u32, i32]),
@@ -292,6 +293,20 @@ class Context:
         _check(lib().dctc_carver_resize_width(self._h, int(n_seams), _ptr(seams) if n_seams else None),
                "dctc_carver_resize_width")
         return seams
+
+    def preview_energy(self, img, want_image=True):
+        """Preview-path operator (dct_energy_preview, src/render.c:421-501): returns (energy float map, normalised
+        8-bit image with the input's channel count)."""
+        img = np.asarray(img)
+        if img.ndim == 2:
+            img = img[:, :, None]
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w, ch = img.shape
+        en = np.empty((h, w), np.float32)
+        out = np.empty((h, w, ch), np.uint8) if want_image else None
+        _check(lib().dctc_preview_energy(self._h, _ptr(img), w, h, ch, w * ch, _ptr(en), _ptr(out) if want_image else None),
+               "dctc_preview_energy")
+        return en, out
 
     def carver_energy_image(self):
         """8-bit grey energy image of the session's current map (liblqr get_energy_image semantics)."""

@@ -27,6 +27,9 @@ struct DctcK1Args {
     const int* seam;
     float* band_vals;
     int band_r, band_stride;
+    // preview operator (dct_energy_preview_rows, src/render.c:31-60): window offsets -(C-1) .. b-C with C = (b-1)/2
+    // (src/dct.h:8-9), BT.601 byte luminance (src/render.h:5), first transform index walks y (tile kernel only)
+    int preview;
 };
 
 // Band limits of row y for a removed seam (seam[] in the coordinates before removal, w = width after removal).
@@ -60,6 +63,16 @@ __device__ __forceinline__ float dctc_luma255(const uint8_t* __restrict__ p, int
     return v;
 }
 
+// Preview path luminance: RGB2LUMINANCE of src/render.h:5, (guchar)(16.0 + r*0.2568 + g*0.5041 + b*0.0979) evaluated in
+// double in the reference's order and truncated; grey is passed through (src/render.c:62-79).
+__device__ __forceinline__ float dctc_luma_preview(const uint8_t* __restrict__ p, int channels)
+{
+    if (channels < 3) return (float) p[0];
+    const double v = __dadd_rn(__dadd_rn(__dadd_rn(16.0, __dmul_rn((double) p[0], 0.2568)), __dmul_rn((double) p[1], 0.5041)),
+                               __dmul_rn((double) p[2], 0.0979));
+    return (float) (uint8_t) v;
+}
+
 __device__ __forceinline__ const uint8_t* dctc_row_ptr(const DctcK1Args& a, const uint8_t* img, int vy)
 {
     vy = max(-a.top_rows, min(vy, a.h + a.bot_rows - 1));
@@ -86,6 +99,8 @@ struct DctcTracker<true> {   // edges == textures: only the maximum matters
         for (int k2 = 0; k2 < B; k2++)
             if (k1 != 0 || k2 != 0) m = fmaxf(m, fabsf(X[k2]));
     }
+    template <int B>
+    __device__ __forceinline__ void add_t(int k1, const float* X) { add<B>(k1, X); }
     __device__ __forceinline__ float result(float we, float wt) const { (void) we; return m * wt; }
 };
 
@@ -107,6 +122,24 @@ struct DctcTracker<false> {
         } else {
 #pragma unroll
             for (int k2 = 0; k2 < B; k2++) z = fmaxf(z, fabsf(X[k2]));
+        }
+    }
+    // transposed scan (preview path: the first transform index walks y): element (k1, k2) of the x-first layout is
+    // T[k2][k1] of the reference's matrix, so the categories swap roles
+    template <int B>
+    __device__ __forceinline__ void add_t(int k1, const float* X)
+    {
+#pragma unroll
+        for (int k2 = 0; k2 < B; k2++) {
+            const float v = fabsf(X[k2]);
+            if (k2 == 0) {
+                if (k1 == 1) a = v;
+                else if (k1 >= 2) mm = fmaxf(mm, v);
+            } else if (k2 == 1 && k1 == 0) {
+                bv = v;
+            } else {
+                z = fmaxf(z, v);
+            }
         }
     }
     __device__ __forceinline__ float result(float we, float wt) const

@@ -18,7 +18,9 @@ template <int B, int TW, int TH, int P, bool UNIFORM>
 __global__ void __launch_bounds__(TW* TH / P) dctc_k1_tile_kernel(const DctcK1Args a)
 {
     constexpr int NT = TW * TH / P;
-    constexpr int R0 = B / 2 - 1;  // samples before the pixel (window offsets -B/2+1 .. B/2, src/render.c:146-147)
+    // samples before the pixel: carver path window offsets -B/2+1 .. B/2 (src/render.c:146-147); preview path
+    // -(C-1) .. B-C with C = (B-1)/2 (src/render.c:43-44, src/dct.h:8-9)
+    const int R0 = a.preview ? (B - 1) / 2 - 1 : B / 2 - 1;
     constexpr int LW = TW + B - 1, LH = TH + B - 1;
     extern __shared__ float smem[];
     float* __restrict__ L = smem;            // [LH][LW] luma
@@ -53,7 +55,8 @@ __global__ void __launch_bounds__(TW* TH / P) dctc_k1_tile_kernel(const DctcK1Ar
         const int ly = i / LW, lx = i - ly * LW;
         const int gx = max(0, min(tx0 + lx - R0, a.w - 1));
         const uint8_t* row = dctc_row_ptr(a, img, ty0 + ly - R0);
-        L[i] = dctc_luma255(row + (size_t) gx * a.channels, a.channels);
+        const uint8_t* px = row + (size_t) gx * a.channels;
+        L[i] = a.preview ? dctc_luma_preview(px, a.channels) : dctc_luma255(px, a.channels);
     }
     __syncthreads();
 
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(TW* TH / P) dctc_k1_tile_kernel(const DctcK1Ar
         for (int p = 0; p < P; p++) {
             float X[B];
             dctc_dct_fwd<B>(col + p, X);
-            tr[p].template add<B>(k1, X);
+            if (a.preview) tr[p].template add_t<B>(k1, X); else tr[p].template add<B>(k1, X);
         }
     }
     const int gx = tx0 + x;

@@ -158,6 +158,17 @@ int dctc_energy_image_dev(dctc_context *ctx, const float *d_en, size_t en_pitch,
 /* Energy image of the carver session's current map, copied to the host (w*h bytes, pitch w). */
 int dctc_carver_energy_image(dctc_context *ctx, uint8_t *out);
 
+/* ---- preview path --------------------------------------------------------------------------------------
+ * Replaces dct_energy_preview (src/render.c:421-501), the GIMP preview / "energy image" filter: the same operator
+ * with the preview window (offsets -(C-1) .. b-C, C = (b-1)/2, src/render.c:43-44 and src/dct.h:8-9), BT.601 byte
+ * luminance (RGB2LUMINANCE, src/render.h:5; channels 1, 3 or 4 as convert_row_to_luminance accepts), weights applied
+ * on the 0..255 scale, first transform index along y (src/render.c:47-51); then normalize_image
+ * (src/render.c:81-109).  energy_out (w*h floats, may be NULL) receives the un-normalised map, image_out
+ * (w*h*channels bytes, may be NULL) the normalised image replicated to every channel.  Uses the context's
+ * blocksize / edges / textures (any block size). */
+int dctc_preview_energy(dctc_context *ctx, const uint8_t *img, int w, int h, int channels, size_t pitch_bytes,
+                        float *energy_out, uint8_t *image_out);
+
 /* ---- per-pixel symbol, kept for ABI parity ---------------------------------------------------------------
  * Same signature as the reference's LqrEnergyFunc dct_pixel_energy (src/render.c:134).  `extra_data` must
  * point to a DctcCarverEnergyParams.  A per-pixel call cannot be GPU-backed, so it is served from the host

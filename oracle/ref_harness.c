@@ -122,3 +122,48 @@ int dctc_ref_energy_image(const uint8_t *img, int w, int h, int channels, size_t
     free(luma);
     return 0;
 }
+
+/* ---- preview path: the reference's own dct_energy_preview_rows / convert_row_to_luminance / normalize_image
+ * (render.c:31-109, made linkable by oracle/Makefile), driven the way dct_energy_preview does (render.c:459-482):
+ * a sliding set of `blocksize` luminance rows, row i of the first set = image row clamp(i - (CENTER_ROW - 1)). */
+typedef struct {            /* PlugInVals, layout restated from main.h:12-22 */
+    gfloat edges;
+    gfloat textures;
+    gint blocksize;
+    gint seams_number;
+    gint new_layer, resize_canvas, output_energy, output_seams, vertically;
+} RefPlugInVals;
+void dct_energy_preview_rows(RefPlugInVals *vals, guchar **current_rows, gdouble *energy_image, gint row_number, gint width);
+void convert_row_to_luminance(guchar *inrow, guchar *outrow, gint channels, gint width);
+void normalize_image(gdouble *energy_image, guchar *output_image, gint height, gint width, gint channels);
+
+int dctc_ref_preview(const uint8_t *img, int w, int h, int channels, size_t pitch, int blocksize, float edges,
+                     float textures, double *energy, uint8_t *out_image)
+{
+    RefPlugInVals vals;
+    guchar **rows;
+    int i, row_number, center = (blocksize - 1) / 2;   /* CENTER_ROW, dct.h:8 */
+    vals.edges = edges; vals.textures = textures; vals.blocksize = blocksize; vals.seams_number = 0;
+    vals.new_layer = vals.resize_canvas = vals.output_energy = vals.output_seams = vals.vertically = 0;
+    rows = (guchar **) malloc(sizeof(guchar *) * blocksize);
+    if (!rows) return -1;
+    for (i = 0; i < blocksize; i++) {
+        int yy = i - (center - 1);
+        yy = yy < 0 ? 0 : (yy > h - 1 ? h - 1 : yy);
+        rows[i] = (guchar *) malloc(w);
+        convert_row_to_luminance((guchar *) img + (size_t) yy * pitch, rows[i], channels, w);
+    }
+    for (row_number = 0; row_number < h; row_number++) {
+        int yy = row_number + blocksize - (center - 1);
+        dct_energy_preview_rows(&vals, rows, energy, row_number, w);
+        free(rows[0]);
+        for (i = 1; i < blocksize; i++) rows[i - 1] = rows[i];
+        if (yy > h - 1) yy = h - 1;
+        rows[blocksize - 1] = (guchar *) malloc(w);
+        convert_row_to_luminance((guchar *) img + (size_t) yy * pitch, rows[blocksize - 1], channels, w);
+    }
+    if (out_image) normalize_image(energy, out_image, h, w, channels);
+    for (i = 0; i < blocksize; i++) free(rows[i]);
+    free(rows);
+    return 0;
+}

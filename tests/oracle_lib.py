@@ -156,3 +156,46 @@ def assert_parity(got, want, rel=REL_TOL, abs_=ABS_TOL):
     bad = d > abs_ + rel * np.abs(want)
     assert not bad.any(), "parity: %d px off, max abs %.3e at %s (got %r want %r)" % (
         bad.sum(), d.max(), np.unravel_index(d.argmax(), d.shape), got.flat[d.argmax()], want.flat[d.argmax()])
+
+
+def ref_preview(img, b=8, edges=0.5, textures=0.5, want_image=True):
+    """The reference's own preview path (dct_energy_preview_rows + convert_row_to_luminance + normalize_image,
+    src/render.c:31-109) driven like dct_energy_preview: returns (energy float64 map, normalised image or None)."""
+    L = ref()
+    if L is None:
+        return None
+    img = _img3(img)
+    h, w, ch = img.shape
+    en = np.zeros((h, w), np.float64)
+    out = np.zeros((h, w, ch), np.uint8) if want_image else None
+    L.dctc_ref_preview.restype = C.c_int
+    rc = L.dctc_ref_preview(img.ctypes.data_as(C.c_void_p), w, h, ch, C.c_size_t(w * ch), b, C.c_float(edges),
+                            C.c_float(textures), en.ctypes.data_as(C.c_void_p),
+                            out.ctypes.data_as(C.c_void_p) if want_image else None)
+    assert rc == 0
+    return en, out
+
+
+def oracle_preview(img, b=8, edges=0.5, textures=0.5):
+    """Oracle restatement of the preview operator: (energy float64 map, luminance bytes)."""
+    L = oracle()
+    img = _img3(img)
+    h, w, ch = img.shape
+    lum = np.zeros((h, w), np.uint8)
+    L.dctc_oracle_preview_luminance(img.ctypes.data_as(C.c_void_p), w, h, ch, C.c_size_t(w * ch), lum.ctypes.data_as(C.c_void_p))
+    en = np.zeros((h, w), np.float64)
+    rc = L.dctc_oracle_preview_energy(lum.ctypes.data_as(C.c_void_p), w, h, b, C.c_float(edges), C.c_float(textures),
+                                      en.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return en, lum
+
+
+def preview_normalize(en, channels):
+    """normalize_image (src/render.c:81-109) in float64: (guchar) ROUND(255 * ((e - min) / (max - min)))."""
+    en = np.asarray(en, np.float64)
+    lo, hi = en.min(), en.max()
+    if hi > lo:
+        v = (255.0 * ((en - lo) / (hi - lo)) + 0.5).astype(np.int64).astype(np.uint8)
+    else:
+        v = np.zeros(en.shape, np.uint8)
+    return np.repeat(v[:, :, None], channels, axis=2)

@@ -1,4 +1,5 @@
 """GPU tests of K2 (carver session: seam removal + incremental band energy) through the C ABI."""
+import os
 import numpy as np
 import pytest
 
@@ -211,3 +212,40 @@ def test_energy_image_export_equals_host_formula(ctx, ch, w, h):
     assert np.array_equal(out, want)
     ctx.dev_free(d_en)
     ctx.dev_free(d_out)
+
+
+PREVIEW_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "preview_golden.npz"))
+
+
+@pytest.mark.parametrize("i", range(sum(1 for k in PREVIEW_GOLD.files if k.startswith("img_"))))
+def test_preview_path_against_reference_golden(ctx, i):
+    """dctc_preview_energy vs the reference's own dct_energy_preview_rows / normalize_image outputs
+    (tests/golden/preview_golden.npz, generated from oracle/_ref by tests/golden/make_golden_preview.py).
+    Energies live on the 0..255 luminance scale: |err| <= 255e-6 + 4e-6*|ref|; with edges != textures a near-tie
+    between the classes may flip (same rule as the carver path); the 8-bit image may differ by one level where the
+    FP32 energy sits on a rounding boundary."""
+    img = PREVIEW_GOLD["img_%02d" % i]
+    want = PREVIEW_GOLD["en_%02d" % i].astype(np.float64)
+    want_img = PREVIEW_GOLD["out_%02d" % i]
+    b = int(PREVIEW_GOLD["meta_%02d" % i][0])
+    e, t = (float(v) for v in PREVIEW_GOLD["wts_%02d" % i])
+    ctx.set_params(b, e, t)
+    en, out = ctx.preview_energy(img)
+    ok = np.abs(en.astype(np.float64) - want) <= 255e-6 + 4e-6 * np.abs(want)
+    if e == t:
+        assert ok.all(), (np.abs(en - want).max(), (~ok).sum())
+    else:
+        assert ok.mean() >= 0.995, (~ok).sum()
+    assert out.shape == want_img.shape
+    assert (out[..., 0:1] == out).all()
+    diff = np.abs(out.astype(int) - want_img.astype(int))
+    if e == t:
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.01
+    ctx.set_params(8, 0.5, 0.5)
+
+
+def test_preview_path_rejects_two_channels(ctx):
+    img = np.zeros((4, 4, 2), np.uint8)
+    with pytest.raises(dc.DctcError) as e:
+        ctx.preview_energy(img)
+    assert e.value.status == dc.ERR_INVALID     # convert_row_to_luminance: "Number of channels not 1 or 3"

@@ -122,3 +122,42 @@ def test_preview_operator_window_and_luminance():
     T = np.abs(B @ D @ B.T)
     T[0, 0] = 0
     assert abs(out[y, x] - 0.5 * T.max()) < 1e-9
+
+
+@pytest.mark.parametrize("b", [2, 4, 8, 16])
+@pytest.mark.parametrize("wts", [(0.5, 0.5), (0.8, 0.2)])
+@pytest.mark.parametrize("ch,w,h", [(3, 37, 29), (1, 24, 20), (4, 18, 9)])
+def test_preview_oracle_pinned_to_reference(b, wts, ch, w, h):
+    """The oracle's preview restatement against the reference's OWN dct_energy_preview_rows /
+    convert_row_to_luminance / normalize_image (src/render.c:31-109), driven like dct_energy_preview."""
+    if ol.ref() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    img = ol.synth_image(w, h, ch, 40 + b, 0)
+    en_ref, img_ref = ol.ref_preview(img, b, *wts)
+    en_orc, lum = ol.oracle_preview(img, b, *wts)
+    # the preview map holds float results of weighted_max_dct_correlation stored in doubles
+    assert np.array_equal(en_ref.astype(np.float32).astype(np.float64), en_ref)
+    # the energies are O(100) on the 0..255 luminance scale: agreement to a float ulp, up to class flips on exact ties
+    close = np.abs(en_orc - en_ref) <= 2e-5 * np.maximum(np.abs(en_ref), 1.0)
+    assert close.mean() > 0.995, (~close).sum()
+    if wts[0] == wts[1]:
+        assert close.all()
+    assert np.array_equal(ol.preview_normalize(en_ref, ch), img_ref)
+
+
+def test_preview_golden_fixture_matches_oracle():
+    """The committed preview fixture (generated from the compiled reference) against the oracle restatement, so the
+    check also runs where /root/reference is absent."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preview_golden.npz"))
+    n = sum(1 for k in g.files if k.startswith("img_"))
+    assert n >= 8
+    for i in range(n):
+        img = g["img_%02d" % i]
+        b = int(g["meta_%02d" % i][0])
+        e, t = (float(v) for v in g["wts_%02d" % i])
+        en, _ = ol.oracle_preview(img, b, e, t)
+        want = g["en_%02d" % i].astype(np.float64)
+        close = np.abs(en - want) <= 2e-5 * np.maximum(np.abs(want), 1.0)
+        assert close.mean() > 0.995 and (e != t or close.all()), i
+        assert np.array_equal(ol.preview_normalize(want, img.shape[2] if img.ndim == 3 else 1), g["out_%02d" % i])
