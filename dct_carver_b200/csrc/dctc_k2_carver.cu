@@ -70,122 +70,195 @@ __global__ void __launch_bounds__(NT) dctc_carve_rows_kernel(uint8_t* __restrict
 //   m[0][x] = en[0][x];  m[y][x] = en[y][x] + min(m[y-1][x-1], m[y-1][x], m[y-1][x+1])   (FP32, range clipped)
 //   parent of (y, x) = FIRST strict minimum scanning x-1, x, x+1;  seam end = LEFTMOST minimum of the last row.
 // The map is rebuilt from scratch for every seam (same values as liblqr's incremental update_mmap).  Row y depends on
-// the whole row y-1, so the rows are a chain of h barrier-separated steps on ONE SM.  A first version that kept the
-// rows in shared memory was bound by shared-memory bandwidth (measured ~600 clk per 1920-px row); here every thread
-// keeps its four adjacent cells of the previous row in REGISTERS, gets the two neighbouring cells with warp
-// shuffles (warp-edge lanes through a 2-float-per-warp shared exchange), prefetches the energies two rows ahead
-// with 128-bit global loads and writes the cumulative rows to a global float plane.  The parent choice is not
-// recorded: warp 0 re-derives it during the back-track from that plane, in batches of 32 rows -- the path moves at
-// most one column per row, so the 32 rows' 80-float windows around the current column are fetched with independent
-// coalesced loads (one L2 round trip per batch).  Cells right of the image hold +inf, which is the range clipping.
+// the whole row y-1: a chain of h steps.  Versions with one CTA-wide barrier per row cost ~600-950 clk per row
+// (shared-memory bandwidth, then the latency of a 16-warp barrier round); this one removes the per-row barrier with
+// warp-private trapezoids: a warp owns a strip of 128*P columns, keeps the cells of the previous row in registers
+// (4*P adjacent cells per lane) and exchanges neighbours with warp shuffles only.  What the strip's edge lanes
+// cannot see contaminates one more column per row, so after DP_R rows the outer DP_R columns on each side are
+// garbage and the warp publishes only its central 128*P - 2*DP_R columns; every DP_R rows the warps exchange the
+// last row through shared memory (one barrier per DP_R rows) and restart with fresh halos.  Energies are
+// prefetched 8 rows ahead into registers; the cumulative rows go to a global float plane from which warp 0 re-derives
+// the parent choices during the back-track, in batches of 32 rows (the path moves at most one column per row, so the
+// 32 rows' 80-float windows around the current column are fetched with independent coalesced loads).
+// Cells outside the image hold +inf, which reproduces the range clipping.
 #ifndef DP_EXP
 #define DP_EXP 0   // timing experiments only
 #endif
-constexpr int DP_NT = 512;        // threads of the single DP CTA; every thread owns groups of 4 adjacent columns
-constexpr int DP_MAXP = 4;        // groups per thread: widths up to 4 * 512 * 4 = 8192
+constexpr int DP_R = 16;          // rows between two exchanges = halo columns on each side of a strip
 constexpr int DP_WIN = 80;        // back-track window (floats)
+constexpr int DP_MAXW = 8;        // warps per CTA of the DP cluster (256 threads: room for a deep register prefetch ring)
 
-template <int DP_P>               // column groups per thread of this instantiation (1, 2 or 4)
-__global__ void __launch_bounds__(DP_NT) dctc_seam_dp_kernel(const float* __restrict__ en, size_t en_pitch, int w, int h,
-                                                             float* __restrict__ mplane, size_t m_pitch,
-                                                             int* __restrict__ seam, int* __restrict__ seam_log)
+constexpr int DP_CL = 8;          // CTAs of the cluster the strips are spread over (a lone SM can only pull ~35 GB/s from L2:
+                                  // measured 425 clk per 1920-px row for the energy loads alone, against ~40 clk of math)
+
+__device__ __forceinline__ uint32_t dp_cta_rank()
 {
-    constexpr int NW = DP_NT / 32;
-    __shared__ float edge_l[2][DP_P][NW], edge_r[2][DP_P][NW];   // first / last cell of every warp's span, double buffered
-    __shared__ float red_v[NW];
-    __shared__ int red_i[NW];
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void dp_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a shared-memory location of this CTA's layout) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dp_map(const void* p, uint32_t rank)
+{
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((uint32_t) __cvta_generic_to_shared(p)), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ float4 dp_ld_cluster_v4(uint32_t ra)
+{
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dp_st_cluster_f32(uint32_t ra, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory"); }
+__device__ __forceinline__ void dp_st_cluster_s32(uint32_t ra, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(ra), "r"(v) : "memory"); }
+
+template <int DP_P>               // float4 groups per lane: strip = 128 * DP_P columns, 128 * DP_P - 32 of them published
+__global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dctc_seam_dp_kernel(const float* __restrict__ en, size_t en_pitch, int w, int h,
+                                                                    float* __restrict__ mplane, size_t m_pitch,
+                                                                    int* __restrict__ seam, int* __restrict__ seam_log)
+{
+    constexpr int CPL = 4 * DP_P;                 // cells per lane
+    constexpr int STRIP = 32 * CPL;               // columns a warp computes
+    constexpr int WOUT = STRIP - 2 * DP_R;        // columns a warp publishes
+    constexpr int HL = DP_R / CPL;                // halo lanes on each side (DP_R is a multiple of CPL)
+    constexpr int PF = 16 / DP_P;                 // energy rows in flight per lane (16 float4 registers)
+    extern __shared__ __align__(16) float xrow[]; // two exchange rows of (warps per CTA * WOUT) floats, double buffered
+    __shared__ float red_v[DP_CL * DP_MAXW];      // per-strip minima, gathered in CTA 0 through distributed shared memory
+    __shared__ int red_i[DP_CL * DP_MAXW];
     __shared__ __align__(16) float win[32][DP_WIN];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = 4 * tid;
-    const int W4 = (w + 3) & ~3;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wpc = blockDim.x >> 5;                        // warps (strips) per CTA
+    const uint32_t rank = dp_cta_rank();
+    const int warp = (int) rank * wpc + (tid >> 5);         // strip index across the cluster
+    const int nwarps = DP_CL * wpc;
+    const int xlen = wpc * WOUT;
     const float INF = __int_as_float(0x7f800000);
-    auto load_row = [&](int y, int p) -> float4 {
-        const int xp = x0 + 4 * p * DP_NT;
-        return (y < h && xp < W4) ? __ldg(reinterpret_cast<const float4*>(en + (size_t) y * en_pitch + xp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c0 = warp * WOUT - DP_R + lane * CPL;   // first column of this lane (may be < 0 or >= w)
+    const bool central = lane >= HL && lane < 32 - HL;
+
+    // Per-lane constants of the strip geometry: which groups start inside the image, which of their cells lie right of
+    // it.  Cells outside the image must stay +inf in every row (range clipping); the patch is applied to the computed
+    // row, never to a freshly loaded value -- touching the loaded registers right after the load would turn the
+    // 8-rows-ahead prefetch into a synchronous load (measured: 425 clk per row instead of ~40).
+    bool ld_ok[DP_P];
+    unsigned inf_mask[DP_P];
+#pragma unroll
+    for (int g = 0; g < DP_P; g++) {
+        const int x = c0 + 4 * g;
+        ld_ok[g] = x >= 0 && x < w;              // x is a multiple of 4 and the row pitch covers round_up(w, 4)
+        inf_mask[g] = !ld_ok[g] ? 15u : ((x + 1 >= w ? 2u : 0u) | (x + 2 >= w ? 4u : 0u) | (x + 3 >= w ? 8u : 0u));
+    }
+    auto patch = [&](float4& v, unsigned m) {
+        if (m & 1u) v.x = INF;
+        if (m & 2u) v.y = INF;
+        if (m & 4u) v.z = INF;
+        if (m & 8u) v.w = INF;
     };
-    auto patch_tail = [&](float4& v, int xp) {
-        if (xp >= w) v.x = INF;
-        if (xp + 1 >= w) v.y = INF;
-        if (xp + 2 >= w) v.z = INF;
-        if (xp + 3 >= w) v.w = INF;
-    };
-    constexpr int PF = 8;                 // energy rows in flight per thread (registers): covers the L2 latency of a lone SM
+    // Every lane loads unconditionally (lanes / rows outside the image re-read a valid address and their cells are
+    // patched to +inf): a predicated load is compiled into "load to a temporary + predicated move", i.e. a wait for the
+    // data right after the issue, which again serialises the prefetch.
+    const float* en_g[DP_P];
+#pragma unroll
+    for (int g = 0; g < DP_P; g++) en_g[g] = en + (ld_ok[g] ? c0 + 4 * g : 0);
+    const int hm1 = h - 1;
+
     float4 cur[DP_P], e[PF][DP_P];
 #pragma unroll
-    for (int p = 0; p < DP_P; p++) {
-        const int xp = x0 + 4 * p * DP_NT;
-        cur[p] = load_row(0, p);
-        if (xp < W4) *reinterpret_cast<float4*>(mplane + xp) = cur[p];
-        patch_tail(cur[p], xp);
+    for (int g = 0; g < DP_P; g++) {
+        cur[g] = __ldg(reinterpret_cast<const float4*>(en_g[g]));
+        const int x = c0 + 4 * g;
+        if (central && ld_ok[g]) *reinterpret_cast<float4*>(mplane + x) = cur[g];
+        patch(cur[g], inf_mask[g]);
 #pragma unroll
-        for (int k = 0; k < PF; k++) e[k][p] = load_row(1 + k, p);     // e[k] holds row y with (y - 1) % PF == k
-        if (lane == 0) edge_l[0][p][warp] = cur[p].x;
-        if (lane == 31) edge_r[0][p][warp] = cur[p].w;
+        for (int k = 0; k < PF; k++)               // e[k] holds row y with (y - 1) % PF == k
+            e[k][g] = __ldg(reinterpret_cast<const float4*>(en_g[g] + (size_t) min(1 + k, hm1) * en_pitch));
     }
-    __syncthreads();
 #ifdef DCTC_SYNC_DEBUG
     const long long dbg_t0 = clock64();
 #endif
-    float* mrow = mplane + m_pitch + x0;
-    for (int yb = 1; yb < h; yb += PF) {
+    float* mrow = mplane + m_pitch;
+    int xb = 0;
+    for (int yb = 1; yb < h; yb += DP_R) {
 #pragma unroll
-        for (int k = 0; k < PF; k++) {
-            const int y = yb + k;
+        for (int kk = 0; kk < DP_R; kk++) {
+            const int k = kk % PF;
+            const int y = yb + kk;
             if (y < h) {                                                    // uniform across the CTA
-                const int rb = (y - 1) & 1, wb = y & 1;
+                // neighbours across lanes; the strip's outermost lanes see +inf (their cells are never published)
+                float l = __shfl_up_sync(0xffffffffu, cur[DP_P - 1].w, 1);
+                float r = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
+                if (lane == 0) l = INF;
+                if (lane == 31) r = INF;
+                float4 o[DP_P];
 #pragma unroll
-                for (int p = 0; p < DP_P; p++) {
-                    const int xp = x0 + 4 * p * DP_NT;
-                    const float4 ee = e[k][p];
+                for (int g = 0; g < DP_P; g++) {
+                    const float lg = g == 0 ? l : cur[g > 0 ? g - 1 : 0].w;
+                    const float rg = g == DP_P - 1 ? r : cur[g < DP_P - 1 ? g + 1 : g].x;
+                    o[g].x = e[k][g].x + fminf(fminf(lg, cur[g].x), cur[g].y);
+                    o[g].y = e[k][g].y + fminf(fminf(cur[g].x, cur[g].y), cur[g].z);
+                    o[g].z = e[k][g].z + fminf(fminf(cur[g].y, cur[g].z), cur[g].w);
+                    o[g].w = e[k][g].w + fminf(fminf(cur[g].z, cur[g].w), rg);
+                }
+                // refill the ring slot just consumed with the row PF ahead (issued after the last use of the slot, so
+                // the load targets the slot's registers directly; they are not touched again for PF rows)
 #if !(DP_EXP & 1)
-                    e[k][p] = load_row(y + PF, p);                          // PF rows ahead: off the chain
+#pragma unroll
+                for (int g = 0; g < DP_P; g++)
+                    e[k][g] = __ldg(reinterpret_cast<const float4*>(en_g[g] + (size_t) min(y + PF, hm1) * en_pitch));
 #endif
-                    float l = __shfl_up_sync(0xffffffffu, cur[p].w, 1);
-                    float r = __shfl_down_sync(0xffffffffu, cur[p].x, 1);
-                    // warp-edge lanes take their neighbour from the shared exchange; every lane issues the (broadcast)
-                    // loads so that the row chain stays free of divergent branches
-                    const bool has_l = warp > 0 || p > 0, has_r = warp < NW - 1 || p < DP_P - 1;
-                    const float el = edge_r[rb][warp > 0 ? p : (p > 0 ? p - 1 : 0)][warp > 0 ? warp - 1 : NW - 1];
-                    const float er = edge_l[rb][warp < NW - 1 ? p : (p < DP_P - 1 ? p + 1 : p)][warp < NW - 1 ? warp + 1 : 0];
-                    l = lane == 0 ? (has_l ? el : INF) : l;
-                    r = lane == 31 ? (has_r ? er : INF) : r;
-                    float4 o;
-                    o.x = ee.x + fminf(fminf(l, cur[p].x), cur[p].y);
-                    o.y = ee.y + fminf(fminf(cur[p].x, cur[p].y), cur[p].z);
-                    o.z = ee.z + fminf(fminf(cur[p].y, cur[p].z), cur[p].w);
-                    o.w = ee.w + fminf(fminf(cur[p].z, cur[p].w), r);
+#pragma unroll
+                for (int g = 0; g < DP_P; g++) {
 #if DP_EXP & 2
-                    if (o.x == 12345.678f)
+                    if (o[g].x == 12345.678f)
 #endif
-                    if (xp < W4) *reinterpret_cast<float4*>(mrow + 4 * p * DP_NT) = o;
-                    if (xp + 4 > w) patch_tail(o, xp);                      // cells right of the image stay +inf
-                    cur[p] = o;
-                    if (lane == 0) edge_l[wb][p][warp] = o.x;
-                    if (lane == 31) edge_r[wb][p][warp] = o.w;
+                    if (central && ld_ok[g]) *reinterpret_cast<float4*>(mrow + (c0 + 4 * g)) = o[g];
+                    patch(o[g], inf_mask[g]);                               // cells outside the image stay +inf
+                    cur[g] = o[g];
                 }
                 mrow += m_pitch;
-#if DP_EXP & 4
-                __syncwarp();
-#else
-                __syncthreads();
-#endif
             }
+        }
+        // exchange the last row of the block: every warp publishes its central cells, then reloads its whole strip
+        if (yb + DP_R < h && !(DP_EXP & 4)) {
+            float* xr = xrow + xb * xlen;                 // this CTA's segment: columns [rank * xlen, (rank + 1) * xlen)
+            if (central) {
+#pragma unroll
+                for (int g = 0; g < DP_P; g++) *reinterpret_cast<float4*>(xr + (c0 + 4 * g - (int) rank * xlen)) = cur[g];
+            }
+            dp_cluster_sync();
+#pragma unroll
+            for (int g = 0; g < DP_P; g++) {
+                const int x = c0 + 4 * g;
+                if (x >= 0 && x < w) {   // published cells right of the image are already +inf
+                    const int owner = x / xlen;                                   // a float4 never straddles two strips
+                    cur[g] = dp_ld_cluster_v4(dp_map(xr + (x - owner * xlen), (uint32_t) owner));
+                } else {
+                    cur[g] = make_float4(INF, INF, INF, INF);
+                }
+            }
+            xb ^= 1;
         }
     }
 #ifdef DCTC_SYNC_DEBUG
     const long long dbg_t1 = clock64();
 #endif
-    // leftmost minimum of the last row
+    // leftmost minimum of the last row (central cells only: the others are either duplicates or contaminated)
     float bv = INF;
     int bi = 0x7fffffff;
+    if (central) {
 #pragma unroll
-    for (int p = 0; p < DP_P; p++) {
-        const int xp = x0 + 4 * p * DP_NT;
-        const float c4[4] = {cur[p].x, cur[p].y, cur[p].z, cur[p].w};
+        for (int g = 0; g < DP_P; g++) {
+            const float c4[4] = {cur[g].x, cur[g].y, cur[g].z, cur[g].w};
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int x = xp + k;
-            if (x < w && (c4[k] < bv || bi == 0x7fffffff)) { bv = c4[k]; bi = x; }   // ascending x per thread: strict < keeps the leftmost
+            for (int k = 0; k < 4; k++) {
+                const int x = c0 + 4 * g + k;
+                if (x >= 0 && x < w && (c4[k] < bv || bi == 0x7fffffff)) { bv = c4[k]; bi = x; }   // ascending x: strict < keeps the leftmost
+            }
         }
     }
 #pragma unroll
@@ -194,11 +267,14 @@ __global__ void __launch_bounds__(DP_NT) dctc_seam_dp_kernel(const float* __rest
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
     }
-    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
-    __syncthreads();   // also orders this CTA's global writes of the cumulative plane before warp 0 reads them back
-    if (tid < 32) {
-        bv = tid < NW ? red_v[tid] : INF;
-        bi = tid < NW ? red_i[tid] : 0x7fffffff;
+    if (lane == 0) { dp_st_cluster_f32(dp_map(&red_v[warp], 0u), bv); dp_st_cluster_s32(dp_map(&red_i[warp], 0u), bi); }
+    dp_cluster_sync();   // release/acquire at cluster scope: also orders every CTA's global writes of the cumulative plane
+    if (rank == 0 && tid < 32) {
+        bv = INF;
+        bi = 0x7fffffff;
+        for (int i = tid; i < nwarps; i += 32) {   // strips in ascending column order: strict < keeps the leftmost
+            if (red_i[i] != 0x7fffffff && (bi == 0x7fffffff || red_v[i] < bv)) { bv = red_v[i]; bi = red_i[i]; }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -213,16 +289,19 @@ __global__ void __launch_bounds__(DP_NT) dctc_seam_dp_kernel(const float* __rest
             // the parents of rows ytop, ytop-1, ... are chosen in rows ytop-1, ytop-2, ...: window row i = image row ytop-1-i
             int base = (x - 36) & ~3;
             base = base < 0 ? 0 : (base > max_base ? max_base : base);
-            float4 t[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const int yy = ytop - 1 - i;
-                t[i] = (yy >= 0 && lane < DP_WIN / 4) ? __ldcg(reinterpret_cast<const float4*>(mplane + (size_t) yy * m_pitch + base) + lane)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (lane < DP_WIN / 4) {
+            for (int hh = 0; hh < 2; hh++) {     // two chunks of 16 rows: 16 independent coalesced loads in flight per lane
+                float4 t[16];
 #pragma unroll
-                for (int i = 0; i < 32; i++) reinterpret_cast<float4*>(win[i])[lane] = t[i];
+                for (int i = 0; i < 16; i++) {
+                    const int yy = ytop - 1 - (16 * hh + i);
+                    t[i] = (yy >= 0 && lane < DP_WIN / 4) ? __ldcg(reinterpret_cast<const float4*>(mplane + (size_t) yy * m_pitch + base) + lane)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (lane < DP_WIN / 4) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) reinterpret_cast<float4*>(win[16 * hh + i])[lane] = t[i];
+                }
             }
             __syncwarp();
             const int steps = ytop < 32 ? ytop : 32;
@@ -390,7 +469,7 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     if (n_seams == 0) return DCTC_OK;
     if (n_seams >= ctx->c_w) return DCTC_ERR_STATE;
     const int h = ctx->c_h, r = ctx->blocksize / 2, bs = band_stride(ctx);
-    if (ctx->c_w > 4 * DP_NT * DP_MAXP) return DCTC_ERR_UNSUPPORTED;   // wider than one CTA's columns: use the host seam loop
+    if (ctx->c_w > DP_CL * DP_MAXW * (512 - 2 * DP_R)) return DCTC_ERR_UNSUPPORTED;   // wider than the cluster's strips: use the host seam loop
     CK(ctx, cudaSetDevice(ctx->device));
     // cumulative-map plane, rows padded so that the 80-float back-track windows stay inside
     const size_t m_pitch = ctx->c_en_pitch < (size_t) DP_WIN ? (size_t) DP_WIN : ctx->c_en_pitch;
@@ -404,13 +483,20 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         CK(ctx, cudaMalloc((void**) &ctx->c_seam_log, sizeof(int) * (size_t) n_seams * h));
         ctx->c_seam_log_cap = (size_t) n_seams * h;
     }
-    const size_t w4 = ((size_t) ctx->c_w + 3) & ~(size_t) 3;
-    const int groups = (int) ((w4 / 4 + DP_NT - 1) / DP_NT);
-    auto dp = groups <= 1 ? dctc_seam_dp_kernel<1> : groups <= 2 ? dctc_seam_dp_kernel<2> : dctc_seam_dp_kernel<4>;
+    // strip geometry: 128*P columns per warp, 128*P - 2*DP_R published; the strips are spread over a cluster of DP_CL CTAs
+    const int wcur = ctx->c_w;
+    const int cap = DP_CL * DP_MAXW;
+    const int P = wcur <= cap * (128 - 2 * DP_R) ? 1 : wcur <= cap * (256 - 2 * DP_R) ? 2 : 4;
+    const int wout = 128 * P - 2 * DP_R;
+    const int strips = (wcur + wout - 1) / wout;
+    const int wpc = (strips + DP_CL - 1) / DP_CL;
+    const size_t dp_smem = sizeof(float) * 2 * (size_t) wpc * wout;
+    auto dp = P == 1 ? dctc_seam_dp_kernel<1> : P == 2 ? dctc_seam_dp_kernel<2> : dctc_seam_dp_kernel<4>;
+    if (dp_smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dp_smem));
     for (int s = 0; s < n_seams; s++) {
         const int w_old = ctx->c_w;
         // build_mmap + build_vpath
-        dp<<<1, DP_NT, 0, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam,
+        dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam,
                                          ctx->c_seam_log + (size_t) s * h);
 #ifdef DCTC_SYNC_DEBUG
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }
