@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "dctc_carver_load", "dctc_carver_width", "dctc_carver_height", "dctc_carver_energy", "dctc_carve_and_update",
     "dctc_carver_image", "dctc_carver_resize_width", "dctc_pixel_energy",
     "dctc_energy_minmax_dev", "dctc_energy_image_dev", "dctc_carver_energy_image", "dctc_preview_energy",
+    "dctc_carver_set_dump_vmaps", "dctc_carver_vmap", "dctc_carver_paint_seams",
     "dctc_synth_fill_dev", "dctc_synth_byte", "dctc_ipc_export", "dctc_ipc_open", "dctc_ipc_close",
     "dctc_dev_alloc", "dctc_dev_free", "dctc_host_alloc_pinned", "dctc_host_free_pinned", "dctc_memcpy_h2d",
     "dctc_memcpy_d2h", "dctc_memset_dev", "dctc_sync", "dctc_timer_begin", "dctc_timer_end",
@@ -92,6 +93,9 @@ def lib():
         "dctc_energy_image_dev": (i32, [vp, vp, C.c_size_t, i32, i32, vp, vp, C.c_size_t, i32]),
         "dctc_carver_energy_image": (i32, [vp, vp]),
         "dctc_preview_energy": (i32, [vp, vp, i32, i32, i32, C.c_size_t, vp, vp]),
+        "dctc_carver_set_dump_vmaps": (i32, [vp, i32]),
+        "dctc_carver_vmap": (i32, [vp, vp, vp]),
+        "dctc_carver_paint_seams": (i32, [vp, vp, i32, C.c_size_t]),
         "dctc_pixel_energy": (f32, [i32, i32, i32, i32, vp, vp]),
         "dctc_synth_fill_dev": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, u32, i32, i32, i32]),
         "dctc_synth_byte": (C.c_uint8, [u32, u32, u32, u32, u32, i32]),
@@ -307,6 +311,25 @@ class Context:
         _check(lib().dctc_preview_energy(self._h, _ptr(img), w, h, ch, w * ch, _ptr(en), _ptr(out) if want_image else None),
                "dctc_preview_energy")
         return en, out
+
+    def carver_set_dump_vmaps(self, on=True):
+        _check(lib().dctc_carver_set_dump_vmaps(self._h, int(on)), "dctc_carver_set_dump_vmaps")
+
+    def carver_vmap(self, w0, h):
+        """(visibility map of the original w0 x h pixels, depth): removal order per pixel, 0 = never removed."""
+        out = np.empty((h, w0), np.int32)
+        depth = C.c_int(0)
+        _check(lib().dctc_carver_vmap(self._h, _ptr(out), C.byref(depth)), "dctc_carver_vmap")
+        return out, depth.value
+
+    def carver_paint_seams(self, img):
+        """display_carver_seams (src/render.c:204-240) on a copy of the original image."""
+        img = np.array(img, dtype=np.uint8, order="C")
+        if img.ndim == 2:
+            img = img[:, :, None]
+        h, w, ch = img.shape
+        _check(lib().dctc_carver_paint_seams(self._h, _ptr(img), ch, w * ch), "dctc_carver_paint_seams")
+        return img
 
     def carver_energy_image(self):
         """8-bit grey energy image of the session's current map (liblqr get_energy_image semantics)."""

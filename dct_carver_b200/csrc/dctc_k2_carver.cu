@@ -328,6 +328,52 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     }
 }
 
+// ---- visibility map + seam display ---------------------------------------------------
+// liblqr's update_vsmap: the pixel removed from row y by the k-th seam is original column raw[y][s]; its entry of the
+// visibility map becomes k (1-based).  raw is compacted over the seam like the image (one CTA per row).
+__global__ void __launch_bounds__(256) dctc_vs_update_kernel(int* __restrict__ raw, int* __restrict__ vs, int w0,
+                                                             const int* __restrict__ seam, int w_old, int order)
+{
+    const int y = blockIdx.x;
+    int* rrow = raw + (size_t) y * w0;
+    const int s = seam[y];
+    if (threadIdx.x == 0) vs[(size_t) y * w0 + rrow[s]] = order;
+    for (int base = s; base < w_old - 1; base += 256 * 4) {
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = base + k * 256 + threadIdx.x;
+            v[k] = x < w_old - 1 ? rrow[x + 1] : 0;
+        }
+        __syncthreads();   // all loads of this chunk (incl. rrow[s] above) before any store; also orders chunk after chunk
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = base + k * 256 + threadIdx.x;
+            if (x < w_old - 1) rrow[x] = v[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) dctc_iota_rows_kernel(int* __restrict__ raw, int w0, int h)
+{
+    const size_t i = (size_t) blockIdx.x * 256 + threadIdx.x;
+    if (i < (size_t) w0 * h) raw[i] = (int) (i % (size_t) w0);
+}
+
+// display_carver_seams (src/render.c:204-240): for x < w-1, y < h-1, every removed pixel becomes (0, 255*vis/depth, 0)
+__global__ void __launch_bounds__(256) dctc_paint_seams_kernel(uint8_t* __restrict__ img, size_t pitch, int channels, int w, int h,
+                                                               const int* __restrict__ vs, int depth)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= w - 1 || y >= h - 1) return;
+    const int vis = vs[(size_t) y * w + x];
+    if (vis == 0) return;
+    uint8_t* p = img + (size_t) y * pitch + (size_t) x * channels;
+    p[0] = 0;
+    if (channels > 1) p[1] = (uint8_t) (255.0 * ((double) vis) / ((double) depth));
+    if (channels > 2) p[2] = 0;
+}
+
 void dctc_carver_release(dctc_context* ctx)
 {
     if (ctx->c_img) cudaFree(ctx->c_img);
@@ -335,12 +381,14 @@ void dctc_carver_release(dctc_context* ctx)
     if (ctx->c_m) cudaFree(ctx->c_m);
     if (ctx->c_dir) cudaFree(ctx->c_dir);
     if (ctx->c_seam_log) cudaFree(ctx->c_seam_log);
+    if (ctx->c_raw) cudaFree(ctx->c_raw);
+    if (ctx->c_vs) cudaFree(ctx->c_vs);
     if (ctx->c_seam) cudaFree(ctx->c_seam);
     if (ctx->c_band) cudaFree(ctx->c_band);
     if (ctx->c_band_vals) cudaFree(ctx->c_band_vals);
     if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
     if (ctx->h_band) cudaFreeHost(ctx->h_band);
-    ctx->c_img = nullptr; ctx->c_en = nullptr; ctx->c_m = nullptr; ctx->c_dir = nullptr; ctx->c_seam_log = nullptr; ctx->c_seam_log_cap = 0; ctx->c_seam = nullptr; ctx->c_band = nullptr;
+    ctx->c_img = nullptr; ctx->c_en = nullptr; ctx->c_m = nullptr; ctx->c_dir = nullptr; ctx->c_seam_log = nullptr; ctx->c_seam_log_cap = 0; ctx->c_raw = nullptr; ctx->c_vs = nullptr; ctx->c_vs_depth = 0; ctx->c_seam = nullptr; ctx->c_band = nullptr;
     ctx->c_band_vals = nullptr; ctx->h_mirror = nullptr; ctx->h_band = nullptr;
     ctx->c_w0 = ctx->c_w = ctx->c_h = ctx->c_ch = 0;
     ctx->c_pitch = 0;
@@ -471,6 +519,17 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     const int h = ctx->c_h, r = ctx->blocksize / 2, bs = band_stride(ctx);
     if (ctx->c_w > DP_CL * DP_MAXW * (512 - 2 * DP_R)) return DCTC_ERR_UNSUPPORTED;   // wider than the cluster's strips: use the host seam loop
     CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->c_dump_vmaps && !ctx->c_raw) {
+        if (ctx->c_w != ctx->c_w0) return DCTC_ERR_STATE;   // the map must be requested before the first seam is removed
+        const size_t n = (size_t) ctx->c_w0 * h;
+        CK(ctx, cudaMalloc((void**) &ctx->c_raw, sizeof(int) * n));
+        CK(ctx, cudaMalloc((void**) &ctx->c_vs, sizeof(int) * n));
+        CK(ctx, cudaMemsetAsync(ctx->c_vs, 0, sizeof(int) * n, ctx->stream));
+        dctc_iota_rows_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->c_raw, ctx->c_w0, h);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+        ctx->c_vs_depth = 0;
+    }
     // cumulative-map plane, rows padded so that the 80-float back-track windows stay inside
     const size_t m_pitch = ctx->c_en_pitch < (size_t) DP_WIN ? (size_t) DP_WIN : ctx->c_en_pitch;
     if (!ctx->c_m) {
@@ -501,6 +560,10 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
 #ifdef DCTC_SYNC_DEBUG
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }
 #endif
+        if (ctx->c_dump_vmaps) {   // update_vsmap
+            dctc_vs_update_kernel<<<h, 256, 0, ctx->stream>>>(ctx->c_raw, ctx->c_vs, ctx->c_w0, ctx->c_seam, w_old, ++ctx->c_vs_depth);
+            ctx->launches++;
+        }
         // carve: compact image and energy rows over the seam
         dctc_carve_rows_kernel<256, 4><<<h, 256, 0, ctx->stream>>>(ctx->c_img, ctx->c_pitch, ctx->c_ch, ctx->c_en,
                                                                    ctx->c_en_pitch, ctx->c_seam, w_old);
@@ -524,6 +587,49 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     if (seams_out)
         CK(ctx, cudaMemcpyAsync(seams_out, ctx->c_seam_log, sizeof(int) * (size_t) n_seams * h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DCTC_OK;
+}
+
+int dctc_carver_set_dump_vmaps(dctc_context* ctx, int on)
+{
+    if (!ctx) return DCTC_ERR_INVALID;
+    ctx->c_dump_vmaps = on != 0;
+    return DCTC_OK;
+}
+
+int dctc_carver_vmap(dctc_context* ctx, int* vmap_out, int* depth_out)
+{
+    if (!ctx) return DCTC_ERR_INVALID;
+    if (!ctx->c_img || !ctx->c_vs) return DCTC_ERR_STATE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (vmap_out)
+        CK(ctx, cudaMemcpyAsync(vmap_out, ctx->c_vs, sizeof(int) * (size_t) ctx->c_w0 * ctx->c_h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (depth_out) *depth_out = ctx->c_vs_depth;
+    return DCTC_OK;
+}
+
+int dctc_carver_paint_seams(dctc_context* ctx, uint8_t* img, int channels, size_t pitch)
+{
+    if (!ctx || !img || channels < 1 || channels > 4) return DCTC_ERR_INVALID;
+    if (!ctx->c_img || !ctx->c_vs || ctx->c_vs_depth <= 0) return DCTC_ERR_STATE;
+    const int w = ctx->c_w0, h = ctx->c_h;
+    if (pitch < (size_t) w * channels) return DCTC_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    uint8_t* d = nullptr;
+    const size_t dp = ((size_t) w * channels + 15) & ~(size_t) 15;
+    CK(ctx, cudaMalloc((void**) &d, dp * h));
+    cudaError_t e = cudaMemcpy2DAsync(d, dp, img, pitch, (size_t) w * channels, h, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        dctc_paint_seams_kernel<<<dim3((w + 255) / 256, h), 256, 0, ctx->stream>>>(d, dp, channels, w, h, ctx->c_vs, ctx->c_vs_depth);
+        e = cudaGetLastError();
+        ctx->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(img, pitch, d, dp, (size_t) w * channels, h, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) return dctc_fail_cuda(ctx, e);
     return DCTC_OK;
 }
 

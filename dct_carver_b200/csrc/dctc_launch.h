@@ -44,6 +44,12 @@ struct dctc_context {
     int8_t* c_dir = nullptr;       // (unused)
     int* c_seam_log = nullptr;     // seams of dctc_carver_resize_width, n_seams * h
     size_t c_seam_log_cap = 0;
+    // visibility map (lqr_carver_set_dump_vmaps, src/render.c:374): raw = original column of every current pixel,
+    // vs = removal order of every original pixel (0 = never removed); both w0 x h ints, only when requested
+    int* c_raw = nullptr;
+    int* c_vs = nullptr;
+    int c_vs_depth = 0;
+    bool c_dump_vmaps = false;
     int* c_seam = nullptr;         // h entries
     int* c_band = nullptr;         // 2*h entries: xmin, xmax
     float* c_band_vals = nullptr;  // packed band values

@@ -143,6 +143,16 @@ int dctc_carver_image(dctc_context *ctx, uint8_t *out);
  * delta_x = 1, rigidity = 0 (src/render.c:313). */
 int dctc_carver_resize_width(dctc_context *ctx, int n_seams, int *seams_out);
 
+/* ---- visibility map and seam display ------------------------------------------------------------------------
+ * lqr_carver_set_dump_vmaps (src/render.c:374): ask the session to record, for every ORIGINAL pixel, the order in
+ * which dctc_carver_resize_width removed it (1-based, 0 = still visible).  Call before the first seam is removed. */
+int dctc_carver_set_dump_vmaps(dctc_context *ctx, int on);
+/* The map (w0*h ints, row pitch = original width; lqr_vmap_get_data / _get_depth, src/render.c:216-219). */
+int dctc_carver_vmap(dctc_context *ctx, int *vmap_out, int *depth_out);
+/* display_carver_seams (src/render.c:204-240) on a host image of the ORIGINAL size: every removed pixel with
+ * x < w-1, y < h-1 becomes (0, (guchar)(255.0 * vis / depth), 0); painted on the device. */
+int dctc_carver_paint_seams(dctc_context *ctx, uint8_t *img, int channels, size_t pitch_bytes);
+
 /* ---- K3: energy-image export ------------------------------------------------------------------------------
  * Replaces lqr_carver_get_energy_image(carver, buf, orientation, LQR_COLDEPTH_8I, LQR_GREY_IMAGE) as called at
  * src/render.c:191 (the plug-in's "output energy" option, src/render.c:175-202): e -> e/(1+e), min-max normalise,

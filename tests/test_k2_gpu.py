@@ -249,3 +249,35 @@ def test_preview_path_rejects_two_channels(ctx):
     with pytest.raises(dc.DctcError) as e:
         ctx.preview_energy(img)
     assert e.value.status == dc.ERR_INVALID     # convert_row_to_luminance: "Number of channels not 1 or 3"
+
+
+@pytest.mark.parametrize("ch,w,h,n", [(3, 150, 90, 25), (1, 97, 40, 30)])
+def test_device_vmap_and_seam_display_equal_host_carver(ctx, ch, w, h, n):
+    """Visibility map (lqr_carver_set_dump_vmaps + lqr_vmap_get_data, src/render.c:214-219,374) recorded by the device
+    seam loop == the host carver's, and display_carver_seams (src/render.c:204-240) painted on the device == the
+    formula applied to that map."""
+    from dct_carver_b200 import host
+    img = ol.synth_image(w, h, ch, 700 + w, 0)
+    ctx.set_params(8, 0.5, 0.5)
+    want = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, output_seams=True)
+    assert want["vmap"] is not None and want["vmap_depth"] == n
+    ctx.carver_load(img)
+    ctx.carver_set_dump_vmaps(True)
+    ctx.carver_resize_width(n)
+    vmap, depth = ctx.carver_vmap(w, h)
+    ctx.carver_set_dump_vmaps(False)
+    assert depth == n
+    assert np.array_equal(vmap, want["vmap"])
+    assert ((vmap > 0).sum(axis=1) == n).all()
+    painted = ctx.carver_paint_seams(img)
+    ref = img.copy()
+    if ref.ndim == 2:
+        ref = ref[:, :, None]
+    vis = vmap[:h - 1, :w - 1]
+    ys, xs = np.nonzero(vis)
+    ref[ys, xs, 0] = 0
+    if ch > 1:
+        ref[ys, xs, 1] = (255.0 * vis[ys, xs].astype(np.float64) / float(depth)).astype(np.uint8)
+    if ch > 2:
+        ref[ys, xs, 2] = 0
+    assert np.array_equal(painted, ref)
