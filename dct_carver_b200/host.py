@@ -38,6 +38,8 @@ def hostlib():
         L.dctc_render.restype = C.c_int
         L.dctc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(PlugInVals), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.POINTER(RenderResult)]
+        L.dctc_host_set_device_seam_loop.restype = None
+        L.dctc_host_set_device_seam_loop.argtypes = [C.c_int]
         L.dctc_render_result_free.restype = None
         L.dctc_render_result_free.argtypes = [C.POINTER(RenderResult)]
         _host = L
@@ -45,14 +47,16 @@ def hostlib():
 
 
 def render(img, seams_number, blocksize=8, edges=0.5, textures=0.5, vertically=False, ctx=None, callback=None,
-           callback_extra=None, output_energy=False, output_seams=True):
+           callback_extra=None, output_energy=False, output_seams=True, device_loop=True):
     """Retargets `img` by `seams_number` (negative = shrink, as PlugInVals.seams_number) along the width
     (vertically=False) or height.  Energy comes from the GPU context `ctx`, or from a per-pixel `callback`
-    (address of an LqrEnergyFunc; checker use only)."""
+    (address of an LqrEnergyFunc; checker use only).  device_loop=False keeps the cumulative map, seam search and
+    carve on the host (energy batches still on the GPU): the cross-check of the device-resident seam loop."""
     img = np.ascontiguousarray(img, dtype=np.uint8)
     if img.ndim == 2:
         img = img[:, :, None]
     h, w, ch = img.shape
+    hostlib().dctc_host_set_device_seam_loop(int(device_loop))
     vals = PlugInVals(edges, textures, blocksize, seams_number, 0, 1, int(output_energy), int(output_seams), int(vertically))
     res = RenderResult()
     rc = hostlib().dctc_render(img.ctypes.data, w, h, ch, C.byref(vals), ctx.handle if ctx is not None else None,

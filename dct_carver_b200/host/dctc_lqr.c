@@ -29,6 +29,13 @@ struct DctcLqrCarver_ {
     double timing[3];
 };
 
+/* Whether carve_vertical hands the whole seam loop to the device (dctc_carver_resize_width) when a GPU context is
+ * attached.  On by default; the host loop (energy batches on the GPU, cumulative map / seam search / carve here) stays
+ * for widths the device kernel does not cover and as the cross-check the tests run against. */
+static int g_device_seam_loop = 1;
+void dctc_host_set_device_seam_loop(int on) { g_device_seam_loop = on != 0; }
+int dctc_host_get_device_seam_loop(void) { return g_device_seam_loop; }
+
 static double now_s(void)
 {
     struct timespec ts;
@@ -190,6 +197,44 @@ static int carve_vertical(DctcLqrCarver *r, int k, int record_vs)
     if (k <= 0) return DCTC_LQR_OK;
     if (k >= r->w) return DCTC_LQR_ERROR;
     if (!r->gpu && !r->nrg) return DCTC_LQR_ERROR;
+    if (r->gpu && g_device_seam_loop && r->delta_x == 1 && r->rigidity == 0.0f) {
+        /* the whole lqr_carver_resize loop on the device: energy, seam DP, back-track, carve, band update */
+        int drc, *dseams;
+        t0 = now_s();
+        if (r->n_seams + k > r->seams_cap || r->seam_len != h) {
+            int *ns;
+            if (r->seam_len != h) { r->n_seams = 0; r->seam_len = h; }
+            ns = (int *) realloc(r->seams, sizeof(int) * (size_t) (r->n_seams + k) * h);
+            if (!ns) return DCTC_LQR_NOMEM;
+            r->seams = ns; r->seams_cap = r->n_seams + k;
+        }
+        dseams = r->seams + (size_t) r->n_seams * h;
+        if (dctc_carver_load(r->gpu, r->rgb, r->w, h, ch, (size_t) P * ch) != DCTC_OK) return DCTC_LQR_ERROR;
+        r->timing[0] += now_s() - t0;
+        t0 = now_s();
+        dctc_carver_set_dump_vmaps(r->gpu, record_vs);
+        drc = dctc_carver_resize_width(r->gpu, k, dseams);
+        if (drc == DCTC_OK) {
+            const int w1 = r->w - k;
+            if (record_vs) {
+                free(r->vs);
+                r->vs = (int *) calloc((size_t) r->w * h, sizeof(int));
+                if (!r->vs) return DCTC_LQR_NOMEM;
+                r->vs_w = r->w; r->vs_h = h;
+                if (dctc_carver_vmap(r->gpu, r->vs, &r->vs_depth) != DCTC_OK) return DCTC_LQR_ERROR;
+                dctc_carver_set_dump_vmaps(r->gpu, 0);
+            }
+            if (dctc_carver_image(r->gpu, r->rgb) != DCTC_OK) return DCTC_LQR_ERROR;   /* compact rows, pitch = new width */
+            r->n_seams += k;
+            r->w = w1;
+            r->pitch = w1;
+            r->timing[2] += now_s() - t0;
+            return DCTC_LQR_OK;
+        }
+        dctc_carver_set_dump_vmaps(r->gpu, 0);
+        if (drc != DCTC_ERR_UNSUPPORTED) return DCTC_LQR_ERROR;
+        /* wider than the device seam kernel covers: fall through to the host loop (energy still on the GPU) */
+    }
     en = (float *) malloc(sizeof(float) * (size_t) P * h);
     m = (float *) malloc(sizeof(float) * (size_t) P * h);
     raw = (int *) malloc(sizeof(int) * (size_t) P * h);

@@ -120,4 +120,9 @@ typedef DctcLqrEnergyFunc LqrEnergyFunc;
 #ifdef __cplusplus
 }
 #endif
+/* Process-wide switch: hand the seam loop of dctc_lqr_carver_resize to the device (default) or keep the host loop
+ * with GPU energy batches (cross-check, and automatic fallback for widths the device kernel does not cover). */
+void dctc_host_set_device_seam_loop(int on);
+int dctc_host_get_device_seam_loop(void);
+
 #endif

@@ -102,14 +102,15 @@ def _naive(img, b, e, t, n, energy):
     return naive_seams(img, b, e, t, n, energy=energy)
 
 
+@pytest.mark.parametrize("device_loop", [False, True])
 @pytest.mark.parametrize("b,wts", [(8, (0.5, 0.5)), (8, (0.8, 0.2)), (4, (0.5, 0.5)), (16, (0.5, 0.5))])
-def test_gpu_retarget_equals_naive_loop_fed_with_gpu_energy(ctx, b, wts):
+def test_gpu_retarget_equals_naive_loop_fed_with_gpu_energy(ctx, b, wts, device_loop):
     """Incremental GPU energy (K2) + incremental cumulative map must give exactly the seams of the naive loop
     that recomputes the full GPU energy map and the full DP for every seam."""
     from dct_carver_b200 import host
     img = ol.synth_image(150, 90, 3, 321 + b, 0)
     ctx.set_params(b, *wts)
-    got = host.render(img, -25, b, *wts, ctx=ctx)
+    got = host.render(img, -25, b, *wts, ctx=ctx, device_loop=device_loop)
     seams, out = _naive(img, b, *wts, 25, energy=lambda cur: ctx.energy_full(cur))
     assert np.array_equal(got["seams"], seams)
     assert np.array_equal(got["image"], out)
@@ -151,7 +152,7 @@ def test_device_seam_loop_equals_host_carver(ctx, b, ch, w, h, n):
     from dct_carver_b200 import host
     img = ol.synth_image(w, h, ch, 500 + w, 0)
     ctx.set_params(b, 0.5, 0.5)
-    want = host.render(img, -n, b, 0.5, 0.5, ctx=ctx)
+    want = host.render(img, -n, b, 0.5, 0.5, ctx=ctx, device_loop=False)
     ctx.set_params(b, 0.5, 0.5)
     ctx.carver_load(img)
     seams = ctx.carver_resize_width(n)
@@ -259,7 +260,7 @@ def test_device_vmap_and_seam_display_equal_host_carver(ctx, ch, w, h, n):
     from dct_carver_b200 import host
     img = ol.synth_image(w, h, ch, 700 + w, 0)
     ctx.set_params(8, 0.5, 0.5)
-    want = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, output_seams=True)
+    want = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, output_seams=True, device_loop=False)
     assert want["vmap"] is not None and want["vmap_depth"] == n
     ctx.carver_load(img)
     ctx.carver_set_dump_vmaps(True)

@@ -23,7 +23,7 @@ def main():
     host.render(img[:256, :256], -8, ctx=ctx)   # warm-up
     l0 = ctx.launches
     t0 = time.perf_counter()
-    r = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx)
+    r = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, device_loop=False)
     dt = time.perf_counter() - t0
     lh = ctx.launches - l0
     # the same retarget with the whole seam loop on the device (dctc_carver_resize_width)
@@ -37,7 +37,13 @@ def main():
     seams = ctx.carver_resize_width(n)
     dt_dev = time.perf_counter() - t1
     same = bool((seams == r["seams"]).all())
+    # the drop-in path a reference user calls: dctc_render (mirror of render(), src/render.c:327-419) with the device loop
+    t2 = time.perf_counter()
+    r2 = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, device_loop=True)
+    dt_render = time.perf_counter() - t2
+    same = same and bool((r2["seams"] == r["seams"]).all()) and bool((r2["image"] == r["image"]).all())
     print(json.dumps({
+        "dctc_render_device_loop_total_s": dt_render,
         "workload": "1920x1080 RGB -> %dx1080, %d vertical seams, blocksize 8" % (w - n, n),
         "device_loop_total_s": dt_dev, "device_loop_us_per_seam": 1e6 * (dt_dev - t_load) / n,
         "device_loop_load_and_full_map_s": t_load, "device_loop_gpu_launches": ctx.launches - l1,
