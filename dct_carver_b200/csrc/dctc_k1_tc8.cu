@@ -4,7 +4,10 @@
 // ddct8x8s, src/fft2d/shrtdct.c:61-117).  A CTA owns a strip of 128 columns and marches down its segment 8 rows
 // ("a group") at a time; pixel column x0+m is row m of every MMA (TMEM lane m).
 //
-//   producer warps 0-3 (thread = column): cp.async the raw rows of the next group, convert them to luma, run the
+//   converter warps 9-10: cp.async the raw rows two groups ahead (triple-buffered), convert one group to luma
+//       (four pixels x two rows per task: 32-bit shared loads, PRMT + FADD byte->float, no XU-pipe conversions) and
+//       hand the luma row pairs to the producers through hardware named barriers (double-buffered)
+//   producer warps 0-3 (thread = column): run the
 //       x-pass (one packed FP32x2 DCT-8 per row pair), split each coefficient H[k1] into fp16 hi + fp16 lo
 //       (hi = rn16(H), lo = rn16(H - hi): 22 significant bits) and store the group into the TMEM A operand ring
 //       with tcgen05.st: columns [k1][hi|lo][slot g&1][row pair], two consecutive rows per 32-bit column
@@ -26,9 +29,26 @@
 
 namespace {
 
+// -DDCTC_TC_TIMING: per-role wait-cycle accounting (clock64), printed by CTA 0 when it retires (tools/time_tc.py)
+#ifdef DCTC_TC_TIMING
+#define TT_T0() const long long tt_b = clock64()
+#define TT_ACC(role, k) g_tt_acc[k] += clock64() - tt_b
+#define TT_DECL() long long g_tt_acc[4] = {0, 0, 0, 0}; const long long tt_start = clock64()
+#define TT_REPORT(role, cond)                                                                                          \
+    if (blockIdx.x == 0 && (cond))                                                                                     \
+        printf("role %d: total %lld clk, waits %lld %lld %lld %lld\n", role, clock64() - tt_start, g_tt_acc[0], g_tt_acc[1], g_tt_acc[2], g_tt_acc[3])
+#else
+#define TT_T0()
+#define TT_ACC(role, k)
+#define TT_DECL() long long* const g_tt_acc = nullptr
+#define TT_REPORT(role, cond)
+#endif
+
 constexpr int MW = 128;            // columns per CTA = MMA M
-constexpr int LWP = MW + 8;        // staged luma row: columns x0-3 .. x0+MW+3 (+1 pad)
-constexpr int NTHREADS = 288;      // 4 producer warps, 4 consumer warps, 1 MMA warp
+constexpr int LWP = MW + 8;        // staged luma row: index i <-> column x0-4+i (index 0 is a pad, 1..135 are read)
+constexpr int NTHREADS = 384;      // 4 producer warps, 4 consumer warps, 1 MMA warp, 3 converter warps
+constexpr int NCONV = 96;          // converter threads
+constexpr int NQUAD = 34;          // 4-pixel groups per staged row: columns x0-4 .. x0+131
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t TM_A = 0;       // A ring: (k1*2 + part)*8 + slot*4 + pair
 constexpr uint32_t TM_D = 128;     // two accumulator tiles of 64 columns
@@ -42,9 +62,9 @@ struct RawGeom {
 
 struct alignas(128) TcSmem {
     __half B[4][64 * 16];            // Tz as UMMA K-major no-swizzle operands: [0] Bh, [1] Bl, [2]/[3] the K-swapped copies
-    float2 L[4][LWP];                // luma of the current group: [row pair][column], .x = even row
-    uint8_t Raw[2][8 * RawGeom<3>::ROW];
-    uint64_t bar_a_full, bar_a_free, bar_d_full[2], bar_d_free[2];
+    float2 L[2][4][LWP];             // luma of two groups: [buffer][row pair][column], .x = even row
+    uint8_t Raw[3][8 * RawGeom<3>::ROW];
+    uint64_t bar_a_full, bar_a_free, bar_a_free_lo, bar_d_full[2];
     uint32_t tmem_base;
     int work;
 };
@@ -75,14 +95,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
         ".reg .u32 n;\n"
         "mov.u32 n, 0;\n"
         "DCTC_WAIT:\n"
-#if DCTC_TC_WAITMODE == 1
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-#endif
+        "@p bra DCTC_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DCTC_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DCTC_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DCTC_DONE;\n"
         "add.u32 n, n, 1;\n"
-        "setp.lt.u32 p, n, 0x400000;\n"
+        "setp.lt.u32 p, n, 0x100000;\n"
         "@p bra DCTC_WAIT;\n"
         "trap;\n"
         "DCTC_DONE:\n"
@@ -97,7 +119,12 @@ __device__ __forceinline__ bool elect_one()
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Named barriers: 2,3 accumulator tiles; 4 converter threads; 5,6 luma buffer full; 7,8 luma buffer free.
+__device__ __forceinline__ void bar_converters() { asm volatile("bar.sync 4, 96;" ::: "memory"); }
+__device__ __forceinline__ void bar_lfull_arrive(int b) { asm volatile("bar.arrive %0, 224;" ::"r"(5 + b) : "memory"); }
+__device__ __forceinline__ void bar_lfull_sync(int b) { asm volatile("bar.sync %0, 224;" ::"r"(5 + b) : "memory"); }
+__device__ __forceinline__ void bar_lfree_arrive(int b) { asm volatile("bar.arrive %0, 224;" ::"r"(7 + b) : "memory"); }
+__device__ __forceinline__ void bar_lfree_sync(int b) { asm volatile("bar.sync %0, 224;" ::"r"(7 + b) : "memory"); }
 // Accumulator tile t is handed back to the MMA warp through hardware named barrier 2+t (4 consumer warps arrive, the
 // MMA warp syncs: 160 threads): the wake-up is immediate, unlike polling an mbarrier from the issuing thread.
 __device__ __forceinline__ void bar_tile_arrive(int t) { asm volatile("bar.arrive %0, 160;" ::"r"(2 + t) : "memory"); }
@@ -126,58 +153,141 @@ __device__ __forceinline__ void tmem_st_x2(uint32_t taddr, uint32_t r0, uint32_t
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
 }
+// 64 consecutive TMEM columns -> registers as two 32-column loads and one wait (a single .x64 needs 82 registers at its
+// point of issue, which ptxas checks against the launch-time register target, not the setmaxnreg value of the region)
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t (&v)[64])
 {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                 : "r"(taddr + 32u));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ---- staging (producer warps; same scheme as dctc_k1_march8.cu) ------------------------------------------------
+// ---- staging + conversion (converter warps) ----------------------------------------------------------------------
 // The raw interleaved bytes [x0*CH-16, x0*CH+(MW+4)*CH) of the 8 rows of a group are copied global -> shared with
-// 16-byte cp.async one group ahead of their conversion (x0*CH is 16-byte aligned: x0 is a multiple of 128).
+// 16-byte cp.async two groups ahead of their conversion (x0*CH is 16-byte aligned: x0 is a multiple of 128).
 // Chunks outside [0, pitch) are skipped: clamped pixel indices never read them.
+// The chunk -> (row, byte offset) mapping of a converter thread is the same for every group of an item: it is computed
+// once (StageMap) and a group costs one row-pointer lookup and one cp.async per chunk.
 template <int CH>
-__device__ __forceinline__ void stage_raw_async(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R,
-                                                int vy0, int x0, int tid)
-{
-    const int warp = tid >> 5, lane = tid & 31;
-    if (lane < RawGeom<CH>::CHUNKS) {
-        const long long gb = (long long) x0 * CH - 16 + 16 * lane;
-        if (gb >= 0 && gb + 16 <= (long long) a.pitch) {
+struct StageMap {
+    static constexpr int CHUNKS = RawGeom<CH>::CHUNKS;
+    static constexpr int PER = (8 * CHUNKS + NCONV - 1) / NCONV;   // chunks per thread (CH=3: 3, CH=1: 1)
+    int ly[PER];          // row of the group, -1: no copy
+    int soff[PER];        // byte offset inside a raw buffer
+    long long gb[PER];    // byte offset inside the image row
+    __device__ __forceinline__ void init(const DctcK1Args& a, int x0, int ct)
+    {
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const int ly = 2 * warp + r;
-                const uint8_t* src = dctc_row_ptr(a, img, vy0 + ly) + gb;
-                const uint32_t dst = smem_u32(R + ly * RawGeom<CH>::ROW + 16 * lane);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            }
+        for (int i = 0; i < PER; i++) {
+            const int c = ct + i * NCONV;
+            const int r = c / CHUNKS, k = c - r * CHUNKS;
+            gb[i] = (long long) x0 * CH - 16 + 16 * k;
+            soff[i] = r * RawGeom<CH>::ROW + 16 * k;
+            ly[i] = (c < 8 * CHUNKS && gb[i] >= 0 && gb[i] + 16 <= (long long) a.pitch) ? r : -1;
         }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
+    __device__ __forceinline__ void stage(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R, int vy0) const
+    {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            if (ly[i] >= 0) {
+                const uint8_t* src = dctc_row_ptr(a, img, vy0 + ly[i]) + gb[i];
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(R + soff[i])), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+};
+
+// Luma in this kernel is the EXACT integer 2126 R + 7152 G + 722 B (= 10000 * 255 * liblqr's LQR_ER_LUMA value, below
+// 2^22, so its float is exact too); grey is 10000 * v.  Two u8 dot products per pixel (coefficients split into a high
+// and a low byte) replace three byte->float conversions and an FMA chain.  The factor 2^-13 of the scaled x-pass
+// (fp16 range of the hi/lo operands) and the 1/10000 are folded into the final weight.
+constexpr float LUMA_WEIGHT_SCALE = 8192.0f / 10000.0f;
 
 template <int CH>
 __device__ __forceinline__ float luma_raw(const uint8_t* __restrict__ p)
 {
-    if (CH == 3) return fmaf(0.2126f, (float) p[0], fmaf(0.7152f, (float) p[1], 0.0722f * (float) p[2]));
-    return (float) p[0];
+    if (CH == 3) return (float) (2126u * p[0] + 7152u * p[1] + 722u * p[2]);
+    return (float) (10000u * p[0]);
 }
 
-// raw rows -> luma row pairs; staged column lx <-> image column clamp(x0 + lx - 3) (src/render.c:122-132)
+// luma of four consecutive pixels from their CH*4 raw bytes (4-byte aligned); same values as luma_raw
 template <int CH>
-__device__ __forceinline__ void convert_raw(const DctcK1Args& a, const uint8_t* __restrict__ R, float2 (*L)[LWP], int x0, int tid)
+__device__ __forceinline__ void quad_luma(const uint8_t* __restrict__ p, float (&l)[4])
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    if (CH == 3) {
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        constexpr uint32_t CLO = 0x00D2F04Eu, CHI = 0x00021B08u;   // (78, 240, 210, 0), (8, 27, 2, 0): 2126, 7152, 722
+        const uint32_t p1 = __byte_perm(w0, w1, 0x6543), p2 = __byte_perm(w1, w2, 0x5432);
+        l[0] = (float) __dp4a(w0, CLO, __dp4a(w0, CHI, 0u) << 8);
+        l[1] = (float) __dp4a(p1, CLO, __dp4a(p1, CHI, 0u) << 8);
+        l[2] = (float) __dp4a(p2, CLO, __dp4a(p2, CHI, 0u) << 8);
+        l[3] = (float) __dp4a(w2, CLO << 8, __dp4a(w2, CHI << 8, 0u) << 8);
+    } else {
+        const uint32_t w0 = w[0];
+#pragma unroll
+        for (int i = 0; i < 4; i++) l[i] = (float) (10000u * ((w0 >> (8 * i)) & 255u));
+    }
+}
+
+// dctc_dct_fwd2<8> (tools/gen_dct.py) with every constant scaled by 2^-13 (exact), so that the x-pass coefficients of
+// integer luma values up to 2.55e6 stay inside the fp16 range of the hi/lo operand split
+__device__ __forceinline__ void dct8_fwd2_scaled(const float2* __restrict__ v, float2* __restrict__ X)
+{
+    constexpr float S = 1.0f / 8192.0f;
+    const float2 t1 = dctc_f2add(v[0], v[7]), t2 = dctc_f2sub(v[0], v[7]);
+    const float2 t3 = dctc_f2add(v[1], v[6]), t4 = dctc_f2sub(v[1], v[6]);
+    const float2 t5 = dctc_f2add(v[2], v[5]), t6 = dctc_f2sub(v[2], v[5]);
+    const float2 t7 = dctc_f2add(v[3], v[4]), t8 = dctc_f2sub(v[3], v[4]);
+    X[1] = dctc_f2fma(S * 9.754516184e-02f, t8, dctc_f2fma(S * 2.777851224e-01f, t6, dctc_f2fma(S * 4.157347977e-01f, t4, dctc_f2mul(S * 4.903926253e-01f, t2))));
+    X[3] = dctc_f2fma(S * -2.777851224e-01f, t8, dctc_f2fma(S * -4.903926253e-01f, t6, dctc_f2fma(S * -9.754516184e-02f, t4, dctc_f2mul(S * 4.157347977e-01f, t2))));
+    X[5] = dctc_f2fma(S * 4.157347977e-01f, t8, dctc_f2fma(S * 9.754516184e-02f, t6, dctc_f2fma(S * -4.903926253e-01f, t4, dctc_f2mul(S * 2.777851224e-01f, t2))));
+    X[7] = dctc_f2fma(S * -4.903926253e-01f, t8, dctc_f2fma(S * 4.157347977e-01f, t6, dctc_f2fma(S * -2.777851224e-01f, t4, dctc_f2mul(S * 9.754516184e-02f, t2))));
+    const float2 t9 = dctc_f2add(t1, t7), t10 = dctc_f2sub(t1, t7);
+    const float2 t11 = dctc_f2add(t3, t5), t12 = dctc_f2sub(t3, t5);
+    X[2] = dctc_f2fma(S * 1.913417131e-01f, t12, dctc_f2mul(S * 4.619397521e-01f, t10));
+    X[6] = dctc_f2fma(S * -4.619397521e-01f, t12, dctc_f2mul(S * 1.913417131e-01f, t10));
+    const float2 t13 = dctc_f2add(t9, t11), t14 = dctc_f2sub(t9, t11);
+    X[4] = dctc_f2mul(S * 3.535533845e-01f, t14);
+    X[0] = dctc_f2mul(S * 3.535533845e-01f, t13);
+}
+
+// raw rows -> luma row pairs; staged index i <-> image column clamp(x0 - 4 + i) (src/render.c:122-132).
+// A task is one 4-pixel group of one row pair; groups that touch the image border take the per-pixel clamped path.
+template <int CH>
+__device__ __forceinline__ void convert_raw(const DctcK1Args& a, const uint8_t* __restrict__ R, float2 (*L)[LWP], int x0, int ct)
 {
     constexpr int ROW = RawGeom<CH>::ROW;
-    const int b0 = (max(0, min(x0 + tid - 3, a.w - 1)) - x0) * CH + 16;
+    for (int task = ct; task < 4 * NQUAD; task += NCONV) {
+        const int p = task / NQUAD, q = task - p * NQUAD - 1;       // row pair 0..3, quad -1..32
+        const int gx = x0 + 4 * q;
+        const uint8_t* r0 = R + (2 * p) * ROW + 16 + 4 * CH * q;
+        const uint8_t* r1 = r0 + ROW;
+        float l0[4], l1[4];
+        if (gx >= 0 && gx + 3 < a.w) {
+            quad_luma<CH>(r0, l0);
+            quad_luma<CH>(r1, l1);
+        } else {
 #pragma unroll
-    for (int p = 0; p < 4; p++)
-        L[p][tid] = make_float2(luma_raw<CH>(R + (2 * p) * ROW + b0), luma_raw<CH>(R + (2 * p + 1) * ROW + b0));
-    if (tid < 28) {
-        const int p = tid / 7, lx = MW + tid - p * 7;
-        const int b1 = (max(0, min(x0 + lx - 3, a.w - 1)) - x0) * CH + 16;
-        L[p][lx] = make_float2(luma_raw<CH>(R + (2 * p) * ROW + b1), luma_raw<CH>(R + (2 * p + 1) * ROW + b1));
+            for (int i = 0; i < 4; i++) {
+                const int off = (max(0, min(gx + i, a.w - 1)) - gx) * CH;
+                l0[i] = luma_raw<CH>(r0 + off);
+                l1[i] = luma_raw<CH>(r1 + off);
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(&L[p][4 * q + 4]);
+        dst[0] = make_float4(l0[0], l1[0], l0[1], l1[1]);
+        dst[1] = make_float4(l0[2], l1[2], l0[3], l1[3]);
     }
 }
 
@@ -192,34 +302,45 @@ __device__ __forceinline__ void split_pair(float2 x, uint32_t& hi, uint32_t& lo)
 }
 
 // x-pass + split + tcgen05.st of group g (rows staged in s.L) into ring slot g&1; arrives on bar_a_full
-__device__ __forceinline__ void produce_group(TcSmem& s, int g, int tid, uint32_t tmem_lane)
+__device__ __forceinline__ void produce_group(TcSmem& s, int g, int tid, uint32_t tmem_lane, long long* g_tt_acc)
 {
+    (void) g_tt_acc;
     const uint32_t ta = tmem_lane + TM_A + (uint32_t) (g & 1) * 4u;
+    const float2 (*Lg)[LWP] = s.L[g & 1];
+    // the whole x-pass and hi/lo split of the group happens before the ring-slot wait (64 operand registers: the
+    // producer warpgroup runs with 112 registers), so that only the TMEM stores sit between two MMA phases
+    uint32_t hi[8][4], lo[8][4];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-        uint32_t hi[8][2], lo[8][2];
+    for (int p = 0; p < 4; p++) {
+        float2 v[8], X[8];
 #pragma unroll
-        for (int pp = 0; pp < 2; pp++) {
-            const int p = half * 2 + pp;
-            float2 v[8], X[8];
+        for (int j = 0; j < 8; j++) v[j] = Lg[p][tid + j + 1];
+        if (p == 3) bar_lfree_arrive(g & 1);   // last read of this luma buffer
+        dct8_fwd2_scaled(v, X);
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = s.L[p][tid + j];
-            dctc_dct_fwd2<8>(v, X);
+        for (int k1 = 0; k1 < 8; k1++) split_pair(X[k1], hi[k1][p], lo[k1][p]);
+    }
+    // slot g&1 still holds group g-2, read by the MMAs of step g-2: the k1 = 0..3 operands are released when the first
+    // half of those MMAs has completed, the rest at the end of the step
 #pragma unroll
-            for (int k1 = 0; k1 < 8; k1++) split_pair(X[k1], hi[k1][pp], lo[k1][pp]);
-        }
-        if (half == 0 && g >= 2) {
-            // slot g&1 still holds group g-2, read by the MMAs of step g-2: wait for their completion
-            mbar_wait(smem_u32(&s.bar_a_free), (uint32_t) (g & 1));
+    for (int hk = 0; hk < 2; hk++) {
+        if (g >= 2) {
+            TT_T0();
+            mbar_wait(smem_u32(hk ? &s.bar_a_free : &s.bar_a_free_lo), (uint32_t) (g & 1));
+            TT_ACC(0, 1);
             tc_fence_after();
         }
 #pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) {
-            tmem_st_x2(ta + (uint32_t) (k1 * 16 + half * 2), hi[k1][0], hi[k1][1]);
-            tmem_st_x2(ta + (uint32_t) (k1 * 16 + 8 + half * 2), lo[k1][0], lo[k1][1]);
+        for (int k1 = 4 * hk; k1 < 4 * hk + 4; k1++) {
+            tmem_st_x4(ta + (uint32_t) (k1 * 16), hi[k1][0], hi[k1][1], hi[k1][2], hi[k1][3]);
+            tmem_st_x4(ta + (uint32_t) (k1 * 16 + 8), lo[k1][0], lo[k1][1], lo[k1][2], lo[k1][3]);
         }
     }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // warp-wide: every lane's stores have completed
+    {
+        TT_T0();
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // warp-wide: every lane's stores have completed
+        TT_ACC(0, 2);
+    }
     tc_fence_before();
     __syncwarp();
     // Group 0 is not announced on its own: the arrival of group 1 covers both (same warp, program order), so the MMA
@@ -291,13 +412,22 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
 };
 
 template <int K1, bool UNIFORM>
-__device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32_t tmem_lane, bool lane0)
+__device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32_t tmem_lane, bool lane0, long long* g_tt_acc)
 {
+    (void) g_tt_acc;
     constexpr int b = K1 & 1, q = K1 >> 1;
-    mbar_wait(smem_u32(&s.bar_d_full[b]), (uint32_t) (q & 1));
+    {
+        TT_T0();
+        mbar_wait(smem_u32(&s.bar_d_full[b]), (uint32_t) (q & 1));
+        TT_ACC(1, K1 == 0 ? 0 : 1);
+    }
     tc_fence_after();
     uint32_t v[64];
-    tmem_ld_x64(tmem_lane + TM_D + 64u * b, v);
+    {
+        TT_T0();
+        tmem_ld_x64(tmem_lane + TM_D + 64u * b, v);
+        TT_ACC(1, 2);
+    }
     tc_fence_before();
     (void) lane0;
     bar_tile_arrive(b);
@@ -331,63 +461,73 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const uint32_t lane_off = (uint32_t) ((warp & 3) * 32) << 16;
-    bool first = true;
 
-  for (;;) {
-    if (tid == 0) {
-        s.work = atomicAdd(counter, 1);
-        if (!first) {
-            mbar_inval(smem_u32(&s.bar_a_full));
-            mbar_inval(smem_u32(&s.bar_a_free));
-            mbar_inval(smem_u32(&s.bar_d_full[0]));
-            mbar_inval(smem_u32(&s.bar_d_full[1]));
-            mbar_inval(smem_u32(&s.bar_d_free[0]));
-            mbar_inval(smem_u32(&s.bar_d_free[1]));
+    // Every role runs its own copy of the persistent item loop (begin_item / end_item contain the CTA-wide barriers), so
+    // that each warpgroup's whole body follows its setmaxnreg: the 384 threads are launched with 80 registers; the
+    // producers (64 operand registers per group) grow to 104, the consumers to 96, the MMA + converter warpgroup
+    // shrinks to 40.
+    auto begin_item = [&](bool first) -> int {
+        if (tid == 0) {
+            s.work = atomicAdd(counter, 1);
+            if (!first) {
+                mbar_inval(smem_u32(&s.bar_a_full));
+                mbar_inval(smem_u32(&s.bar_a_free));
+                mbar_inval(smem_u32(&s.bar_a_free_lo));
+                mbar_inval(smem_u32(&s.bar_d_full[0]));
+                mbar_inval(smem_u32(&s.bar_d_full[1]));
+            }
+            mbar_init(smem_u32(&s.bar_a_full), 4);
+            mbar_init(smem_u32(&s.bar_a_free), 1);
+            mbar_init(smem_u32(&s.bar_a_free_lo), 1);
+            mbar_init(smem_u32(&s.bar_d_full[0]), 1);
+            mbar_init(smem_u32(&s.bar_d_full[1]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        mbar_init(smem_u32(&s.bar_a_full), 4);
-        mbar_init(smem_u32(&s.bar_a_free), 1);
-        mbar_init(smem_u32(&s.bar_d_full[0]), 1);
-        mbar_init(smem_u32(&s.bar_d_full[1]), 1);
-        mbar_init(smem_u32(&s.bar_d_free[0]), 4);
-        mbar_init(smem_u32(&s.bar_d_free[1]), 4);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    first = false;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const int item = s.work;
-    if (item >= n_items) break;
-    const uint32_t tmem = s.tmem_base;
-    const uint32_t tmem_lane = tmem + lane_off;
-    const int strip = item % strips;
-    const int rest = item / strips;
-    const int seg = rest % segs, frame = rest / segs;
-    const int x0 = strip * MW;
-    const int y0 = seg * seg_rows;
-    const int y1 = min(y0 + seg_rows, a.h);
-    const int nsteps = (y1 - y0 + 7) >> 3;
-    const uint8_t* __restrict__ img = a.img + (size_t) frame * a.frame_stride;
-    float* __restrict__ out = a.out + (size_t) frame * a.out_frame_stride;
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        return s.work;
+    };
+    auto end_item = [&]() {
+        tc_fence_before();
+        __syncthreads();    // every role is done with the barriers, TMEM and staging buffers of this item
+    };
+#define DCTC_ITEM_LOOP                                                                                                 \
+    for (bool first = true;; first = false) {                                                                          \
+        const int item = begin_item(first);                                                                            \
+        if (item >= n_items) break;                                                                                    \
+        const uint32_t tmem = s.tmem_base;                                                                             \
+        const uint32_t tmem_lane = tmem + lane_off;                                                                    \
+        const int strip = item % strips;                                                                               \
+        const int rest = item / strips;                                                                                \
+        const int seg = rest % segs, frame = rest / segs;                                                              \
+        const int x0 = strip * MW;                                                                                     \
+        const int y0 = seg * seg_rows;                                                                                 \
+        const int y1 = min(y0 + seg_rows, a.h);                                                                        \
+        const int nsteps = (y1 - y0 + 7) >> 3;                                                                         \
+        const uint8_t* __restrict__ img = a.img + (size_t) frame * a.frame_stride;                                     \
+        float* __restrict__ out = a.out + (size_t) frame * a.out_frame_stride;                                         \
+        (void) tmem; (void) tmem_lane; (void) x0; (void) y1; (void) img; (void) out;
 
+    TT_DECL();
     if (warp < 4) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        DCTC_ITEM_LOOP
         // ===== producers: group g = virtual rows y0-3+8g .. y0+4+8g; step j consumes groups j and j+1 =====
-        stage_raw_async<CH>(a, img, s.Raw[0], y0 - 3, x0, tid);
-        stage_raw_async<CH>(a, img, s.Raw[1], y0 + 5, x0, tid);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        bar_producers();
-        convert_raw<CH>(a, s.Raw[0], s.L, x0, tid);
-        bar_producers();
-        produce_group(s, 0, tid, tmem_lane);
-        for (int g = 1; g <= nsteps; g++) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            bar_producers();                                  // Raw[g&1] landed everywhere, s.L free
-            if (g + 1 <= nsteps) stage_raw_async<CH>(a, img, s.Raw[(g + 1) & 1], y0 - 3 + 8 * (g + 1), x0, tid);
-            convert_raw<CH>(a, s.Raw[g & 1], s.L, x0, tid);
-            bar_producers();
-            produce_group(s, g, tid, tmem_lane);
+        for (int g = 0; g <= nsteps; g++) {
+            {
+                TT_T0();
+                bar_lfull_sync(g & 1);                        // the converters have written luma buffer g&1
+                TT_ACC(0, 0);
+            }
+            produce_group(s, g, tid, tmem_lane, g_tt_acc);    // arrives on "luma buffer free" after its last read
         }
+        end_item();
+        }
+        TT_REPORT(0, tid == 0);
     } else if (warp < 8) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        DCTC_ITEM_LOOP
         // ===== consumers =====
         const int px = tid - 128;
         const int gx = x0 + px;
@@ -395,33 +535,43 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         for (int st = 0; st < nsteps; st++) {
             TcFold<UNIFORM> f;
             f.init();
-            consume_k1<0, UNIFORM>(s, f, tmem_lane, lane0);
-            consume_k1<1, UNIFORM>(s, f, tmem_lane, lane0);
-            consume_k1<2, UNIFORM>(s, f, tmem_lane, lane0);
-            consume_k1<3, UNIFORM>(s, f, tmem_lane, lane0);
-            consume_k1<4, UNIFORM>(s, f, tmem_lane, lane0);
-            consume_k1<5, UNIFORM>(s, f, tmem_lane, lane0);
-            consume_k1<6, UNIFORM>(s, f, tmem_lane, lane0);
-            consume_k1<7, UNIFORM>(s, f, tmem_lane, lane0);
+            consume_k1<0, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<1, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<2, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<3, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<4, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<5, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<6, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<7, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
             const int gy = y0 + 8 * st;
             if (gx < a.w) {
                 float* __restrict__ o = out + (size_t) gy * a.out_pitch + gx;
                 if (gy + 8 <= y1) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) o[(size_t) i * a.out_pitch] = f.result(i, a.w_edges, a.w_textures);
+                    for (int i = 0; i < 8; i++) o[(size_t) i * a.out_pitch] = f.result(i, a.w_edges * LUMA_WEIGHT_SCALE, a.w_textures * LUMA_WEIGHT_SCALE);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; i++)
-                        if (gy + i < y1) o[(size_t) i * a.out_pitch] = f.result(i, a.w_edges, a.w_textures);
+                        if (gy + i < y1) o[(size_t) i * a.out_pitch] = f.result(i, a.w_edges * LUMA_WEIGHT_SCALE, a.w_textures * LUMA_WEIGHT_SCALE);
                 }
             }
         }
+        end_item();
+        }
+        TT_REPORT(1, tid == 128);
     } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 8) {
+        DCTC_ITEM_LOOP
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc(128, 64);
         const uint64_t bd0 = make_smem_desc(smem_u32(&s.B[0][0]), 128, 256);
         for (int st = 0; st < nsteps; st++) {
-            mbar_wait(smem_u32(&s.bar_a_full), (uint32_t) (st & 1));         // groups st and st+1 are in TMEM
+            {
+                TT_T0();
+                mbar_wait(smem_u32(&s.bar_a_full), (uint32_t) (st & 1));     // groups st and st+1 are in TMEM
+                TT_ACC(2, 0);
+            }
             tc_fence_after();
             // each operand copy is 2048 bytes = 128 descriptor address units
             const uint64_t bh = bd0 + (uint64_t) ((st & 1) ? 256 : 0);
@@ -429,7 +579,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
 #pragma unroll
             for (int k1 = 0; k1 < 8; k1++) {
                 const int b = k1 & 1;
-                if (st > 0 || k1 >= 2) bar_tile_sync(b);     // the consumers have loaded the previous contents of tile b
+                if (st > 0 || k1 >= 2) {
+                    TT_T0();
+                    bar_tile_sync(b);                         // the consumers have loaded the previous contents of tile b
+                    TT_ACC(2, 1);
+                }
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d = tmem + TM_D + 64u * b;
@@ -438,6 +592,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
                     mma_ts(d, al, bh, idesc, 1u);
                     mma_ts(d, ah, bl, idesc, 1u);
                     mma_commit(smem_u32(&s.bar_d_full[b]));
+                    if (k1 == 3 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free_lo));
                     if (k1 == 7 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free));   // waited on by the producers of group st+2
                 }
                 __syncwarp();
@@ -447,10 +602,50 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         // generations start clean for the next work item
         bar_tile_sync(0);
         bar_tile_sync(1);
+        end_item();
+        }
+        TT_REPORT(2, tid == 256);
+        } else {
+        DCTC_ITEM_LOOP
+        // ===== converters: raw rows of group g+2 in flight while group g is converted =====
+        const int ct = tid - (NTHREADS - NCONV);
+        StageMap<CH> sm;
+        sm.init(a, x0, ct);
+        sm.stage(a, img, s.Raw[0], y0 - 3);
+        sm.stage(a, img, s.Raw[1], y0 + 5);
+        int slot = 0;                                         // raw buffer of group g (g % 3)
+        for (int g = 0; g <= nsteps; g++) {
+            {
+                TT_T0();
+                asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of group g have landed
+                TT_ACC(3, 0);
+            }
+            {
+                TT_T0();
+                bar_converters();                             // ... everybody's; raw buffer (g+2)%3 = (g-1)%3 is free
+                TT_ACC(3, 1);
+            }
+            if (g >= 2) {
+                TT_T0();
+                bar_lfree_sync(g & 1);                        // the producers have read group g-2 out of this buffer
+                TT_ACC(3, 2);
+            }
+            convert_raw<CH>(a, s.Raw[slot], s.L[g & 1], x0, ct);
+            bar_lfull_arrive(g & 1);
+            const int nslot = slot == 0 ? 2 : slot - 1;       // (g + 2) % 3
+            if (g + 2 <= nsteps) sm.stage(a, img, s.Raw[nslot], y0 - 3 + 8 * (g + 2));
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            slot = slot == 2 ? 0 : slot + 1;
+        }
+        // the last two groups' "free" arrivals were never waited for: drain them so the next item starts clean
+        bar_lfree_sync((nsteps - 1) & 1);
+        bar_lfree_sync(nsteps & 1);
+        end_item();
+        }
+        TT_REPORT(3, tid == 288);
+        }
     }
-    tc_fence_before();
-    __syncthreads();    // every role is done with the barriers, TMEM and staging buffers of this item
-  }
+#undef DCTC_ITEM_LOOP
 
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "r"(TMEM_COLS));
 }
