@@ -291,14 +291,19 @@ __device__ __forceinline__ void convert_raw(const DctcK1Args& a, const uint8_t* 
     }
 }
 
-// H -> fp16 hi + fp16 lo for two vertically adjacent rows (low half = even row = even K index)
-__device__ __forceinline__ void split_pair(float2 x, uint32_t& hi, uint32_t& lo)
+// H -> fp16 hi and fp16 MINUS lo for two vertically adjacent rows (low half = even row = even K index).
+// hi = rn16(H); the residual comes from one mixed-precision subtract per value (sub.f32.f16 = FHADD: hi - H, exact),
+// so no half->float conversion is needed; the sign is undone by the negate-A bit of the lo*Bh MMA's descriptor.
+__device__ __forceinline__ void split_pair(float2 x, uint32_t& hi, uint32_t& nlo)
 {
     const __half2 h = __floats2half2_rn(x.x, x.y);
-    const float2 r = dctc_f2sub(x, __half22float2(h));
-    const __half2 l = __floats2half2_rn(r.x, r.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+    const uint16_t h0 = (uint16_t) (hi & 0xffffu), h1 = (uint16_t) (hi >> 16);
+    float r0, r1;
+    asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(r0) : "h"(h0), "f"(x.x));
+    asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(r1) : "h"(h1), "f"(x.y));
+    const __half2 l = __floats2half2_rn(r0, r1);
+    nlo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // x-pass + split + tcgen05.st of group g (rows staged in s.L) into ring slot g&1; arrives on bar_a_full
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
                     const uint32_t d = tmem + TM_D + 64u * b;
                     const uint32_t ah = tmem + TM_A + (uint32_t) k1 * 16u, al = ah + 8u;
                     mma_ts(d, ah, bh, idesc, 0u);
-                    mma_ts(d, al, bh, idesc, 1u);
+                    mma_ts(d, al, bh, idesc | (1u << 13), 1u);   // A negated: the ring holds -lo
                     mma_ts(d, ah, bl, idesc, 1u);
                     mma_commit(smem_u32(&s.bar_d_full[b]));
                     if (k1 == 3 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free_lo));
