@@ -166,7 +166,14 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
     }
     cudaError_t e;
     switch (kernel) {
-    case DCTC_KERNEL_FP32_TILE: e = dctc_launch_k1_tile(a, ctx->blocksize, n_frames, uniform, stream); break;
+    case DCTC_KERNEL_FP32_TILE:
+        // block sizes 2 and 4 (HBM-bound): full maps stream through the register-march kernel unless the tile kernel was
+        // asked for explicitly; both produce bit-identical maps
+        e = cudaErrorNotSupported;
+        if (ctx->kernel == DCTC_KERNEL_AUTO && !a.seam && !a.preview && (ctx->blocksize == 2 || ctx->blocksize == 4))
+            e = dctc_launch_k1_small(a, ctx->blocksize, n_frames, uniform, ctx->sm_count, stream);
+        if (e == cudaErrorNotSupported) e = dctc_launch_k1_tile(a, ctx->blocksize, n_frames, uniform, stream);
+        break;
     case DCTC_KERNEL_FP32_MARCH: e = dctc_launch_k1_march8(a, n_frames, uniform, stream); break;
     case DCTC_KERNEL_TC_SPLIT:
         // every launch takes its own work-item counter, so launches in flight on different streams never share one
