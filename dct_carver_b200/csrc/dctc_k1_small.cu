@@ -108,17 +108,18 @@ struct Fold<B, false> {
 // ---- staging ---------------------------------------------------------------------------------------------------
 // raw bytes [x0*CH - 16, x0*CH + (MW + R1)*CH) of 8 rows; chunks outside [0, pitch) are skipped (clamped pixel indices
 // never read them)
-template <int CH, int B>
+template <int CH, int B, int NROWS = 8>
 __device__ __forceinline__ void stage_raw_async(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R,
                                                 int vy0, int x0, int tid)
 {
     using G = RawGeom<CH, B>;
+    constexpr int PER = (NROWS * G::CHUNKS + MW - 1) / MW;
 #pragma unroll
-    for (int i = 0; i < G::PER; i++) {
+    for (int i = 0; i < PER; i++) {
         const int c = tid + i * MW;
         const int ly = c / G::CHUNKS, k = c - ly * G::CHUNKS;
         const long long gb = (long long) x0 * CH - 16 + 16 * k;
-        if (c < 8 * G::CHUNKS && gb >= 0 && gb + 16 <= (long long) a.pitch) {
+        if (c < NROWS * G::CHUNKS && gb >= 0 && gb + 16 <= (long long) a.pitch) {
             const uint8_t* src = dctc_row_ptr(a, img, vy0 + ly) + gb;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(R + ly * G::ROW + 16 * k)), "l"(src) : "memory");
         }
@@ -165,7 +166,7 @@ __device__ __forceinline__ float4 quad_luma(const uint8_t* __restrict__ p)
 // 8 raw rows -> 8 luma rows; staged index i <-> image column clamp(x0 - 4 + i) (src/render.c:122-132).
 // Thread t converts quad t%32 (columns x0+4q .. x0+4q+3) of rows t/32 and t/32+4; the R0 columns left of the strip
 // and the R1 columns right of it are single-pixel tasks of the first threads.
-template <int CH, int B>
+template <int CH, int B, int NROWS = 8>
 __device__ __forceinline__ void convert_raw(const DctcK1Args& a, const uint8_t* __restrict__ R, float* __restrict__ L, int x0, int tid)
 {
     using G = RawGeom<CH, B>;
@@ -173,8 +174,9 @@ __device__ __forceinline__ void convert_raw(const DctcK1Args& a, const uint8_t* 
     const int q = tid & 31, gx = x0 + 4 * q;
     const bool inside = gx + 3 < a.w;
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < (NROWS > 4 ? 2 : 1); i++) {
         const int ly = (tid >> 5) + 4 * i;
+        if (NROWS < 4 && ly >= NROWS) break;
         const uint8_t* r = R + ly * G::ROW + 16 + 4 * CH * q;
         float4 l;
         if (inside) {
@@ -187,7 +189,7 @@ __device__ __forceinline__ void convert_raw(const DctcK1Args& a, const uint8_t* 
         }
         *reinterpret_cast<float4*>(L + ly * LWP + 4 + 4 * q) = l;
     }
-    if (tid < 8 * (R0 + R1)) {
+    if (tid < NROWS * (R0 + R1)) {
         const int ly = tid / (R0 + R1), k = tid - ly * (R0 + R1);
         const int col = k < R0 ? -R0 + k : MW + (k - R0);             // relative to x0
         const int gxc = max(0, min(x0 + col, a.w - 1));
@@ -232,18 +234,19 @@ __device__ __forceinline__ float ypass(const float2 (&H2)[B][B / 2], float we, f
     return f.result(we, wt);
 }
 
-// row r of the chunk: the new image row lands in ring slot (r + B - 1) % B, the window of output row gy+r starts in slot r % B
+// row RW of the chunk: the new image row lands in ring slot (RW + B - 1) % B, the window of output row gy+RW starts in
+// slot RW % B; `o` points at this thread's pixel of that output row
 template <int B, int RW, bool UNIFORM>
 __device__ __forceinline__ void step(float2 (&H2)[B][B / 2], const float* __restrict__ Lbuf, int tid, const DctcK1Args& a,
-                                     float* __restrict__ out, int gx, int gy)
+                                     float* __restrict__ o, bool ok)
 {
     xpass<B, (RW + B - 1) % B>(H2, Lbuf + RW * LWP, tid);
     const float e = ypass<B, RW % B, UNIFORM>(H2, a.w_edges, a.w_textures);
-    if (gx < a.w && gy + RW < a.h) out[(size_t) (gy + RW) * a.out_pitch + gx] = e;
+    if (ok) *o = e;
 }
 
 template <int B, bool UNIFORM, int CH>
-__global__ void __launch_bounds__(MW, 6) dctc_k1_small_kernel(const DctcK1Args a, int seg_rows)
+__global__ void __launch_bounds__(MW, B == 2 ? 8 : 6) dctc_k1_small_kernel(const DctcK1Args a, int seg_rows)
 {
     using G = RawGeom<CH, B>;
     constexpr int R0 = B / 2 - 1, R1 = B / 2;
@@ -256,18 +259,19 @@ __global__ void __launch_bounds__(MW, 6) dctc_k1_small_kernel(const DctcK1Args a
     const uint8_t* __restrict__ img = a.img + (size_t) blockIdx.z * a.frame_stride;
     float* __restrict__ out = a.out + (size_t) blockIdx.z * a.out_frame_stride;
     const int gx = x0 + tid;
+    const bool colok = gx < a.w;
     float2 H2[B][B / 2];
 
     // chunk 0 = virtual rows y0-R0 .. (only the first B-1 are used: prologue); chunk c >= 1 = rows y0+R1+8(c-1) .. +7,
     // which feed output rows y0+8(c-1) .. +7.  Raw buffers rotate over three slots (two chunks in flight).
     const int nchunks = 1 + (y1 - y0 + 7) / 8;
-    stage_raw_async<CH, B>(a, img, Raw[0], y0 - R0, x0, tid);
+    stage_raw_async<CH, B, B - 1>(a, img, Raw[0], y0 - R0, x0, tid);    // the prologue needs B-1 rows only
     stage_raw_async<CH, B>(a, img, Raw[1], y0 + R1, x0, tid);
     if (nchunks > 2) stage_raw_async<CH, B>(a, img, Raw[2], y0 + R1 + 8, x0, tid);
     else asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncthreads();
-    convert_raw<CH, B>(a, Raw[0], L[0], x0, tid);
+    convert_raw<CH, B, B - 1>(a, Raw[0], L[0], x0, tid);
     __syncthreads();
     if (B == 4) {
         xpass<B, 0>(H2, L[0] + 0 * LWP, tid);
@@ -288,14 +292,28 @@ __global__ void __launch_bounds__(MW, 6) dctc_k1_small_kernel(const DctcK1Args a
         float* Lb = L[c & 1];
         convert_raw<CH, B>(a, Raw[slot], Lb, x0, tid);
         __syncthreads();
-        step<B, 0, UNIFORM>(H2, Lb, tid, a, out, gx, gy);
-        step<B, 1, UNIFORM>(H2, Lb, tid, a, out, gx, gy);
-        step<B, 2, UNIFORM>(H2, Lb, tid, a, out, gx, gy);
-        step<B, 3, UNIFORM>(H2, Lb, tid, a, out, gx, gy);
-        step<B, 4, UNIFORM>(H2, Lb, tid, a, out, gx, gy);
-        step<B, 5, UNIFORM>(H2, Lb, tid, a, out, gx, gy);
-        step<B, 6, UNIFORM>(H2, Lb, tid, a, out, gx, gy);
-        step<B, 7, UNIFORM>(H2, Lb, tid, a, out, gx, gy);
+        // one pointer per chunk, advanced by the pitch: no 64-bit multiply and no divergent guard per pixel
+        float* o = out + (size_t) gy * a.out_pitch + gx;
+        const size_t op = a.out_pitch;
+        if (gy + 8 <= a.h) {
+            step<B, 0, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
+            step<B, 1, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
+            step<B, 2, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
+            step<B, 3, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
+            step<B, 4, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
+            step<B, 5, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
+            step<B, 6, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
+            step<B, 7, UNIFORM>(H2, Lb, tid, a, o, colok);
+        } else {
+            step<B, 0, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 0 < a.h); o += op;
+            step<B, 1, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 1 < a.h); o += op;
+            step<B, 2, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 2 < a.h); o += op;
+            step<B, 3, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 3 < a.h); o += op;
+            step<B, 4, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 4 < a.h); o += op;
+            step<B, 5, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 5 < a.h); o += op;
+            step<B, 6, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 6 < a.h); o += op;
+            step<B, 7, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 7 < a.h);
+        }
         slot = slot == 2 ? 0 : slot + 1;
     }
 }
@@ -305,8 +323,9 @@ cudaError_t launch_small(const DctcK1Args& a, int n_frames, bool uniform, int sm
 {
     const int strips = (a.w + MW - 1) / MW;
     // segment height: long segments amortise the prologue, short ones fill the machine for small inputs
+    // (at least ~8 waves of 6-8 resident CTAs per SM keep the tail of the last wave short)
     int seg = 256;
-    while (seg > 16 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 8LL * sm_count) seg >>= 1;
+    while (seg > 32 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 64LL * sm_count) seg >>= 1;
     const int segs = (a.h + seg - 1) / seg;
     if (segs > 65535 || n_frames > 65535) return cudaErrorInvalidConfiguration;
     dim3 grid(strips, segs, n_frames), block(MW);

@@ -180,6 +180,40 @@ def test_row_bands_tensor_core_kernel(ctx, ch, w):
     assert np.array_equal(got, full)
 
 
+@pytest.mark.parametrize("b", [2, 4])
+@pytest.mark.parametrize("wts", [(0.5, 0.5), (0.8, 0.2)])
+@pytest.mark.parametrize("case", [(0, 3, 160, 131), (0, 1, 208, 77), (3, 3, 640, 300), (1, 3, 128, 8), (2, 3, 144, 50),
+                                  (0, 3, 16, 5), (0, 1, 16, 3), (0, 3, 272, 9), (0, 1, 1008, 40)])
+def test_stream_kernel_small_blocks(ctx, b, wts, case):
+    """Block sizes 2 and 4 on 16-byte aligned rows take the streaming register-march kernel (dctc_k1_small.cu): parity
+    with the oracle, and bit-identity with the tile kernel (same FP32 operation order), which serves band updates."""
+    pattern, ch, w, h = case
+    assert (w * ch) % 16 == 0
+    img = ol.synth_image(w, h, ch, 2000 + b, pattern)
+    ctx.set_params(b, *wts)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    got = ctx.energy_full(img)
+    ctx.set_kernel(dc.KERNEL_FP32_TILE)
+    tile = ctx.energy_full(img)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    assert np.array_equal(got.view(np.uint32), tile.view(np.uint32))
+    check_with_flips(got, img, b, *wts)
+
+
+@pytest.mark.parametrize("b", [2, 4])
+@pytest.mark.parametrize("ch,w", [(3, 160), (1, 208)])
+def test_row_bands_stream_kernel(ctx, b, ch, w):
+    """Row bands + halos through the streaming kernel (aligned rows keep every band on its fast path) are bit-equal
+    to the full map."""
+    img = ol.synth_image(w, 131, ch, 23, 0)
+    ctx.set_params(b, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    full = ctx.energy_full(img)
+    got = _band_run(ctx, img, [(0, 13), (13, 50), (50, 51), (51, 131)], b)
+    ol.assert_parity(got, ol.best_energy(img, b, 0.5, 0.5))
+    assert np.array_equal(got, full)
+
+
 def test_full_size_4k_properties(ctx):
     """BASELINE config 2 (3840x2160 RGB) through size-independent properties: (1) random crops re-evaluated by the
     oracle on crop+halo agree in the crop interior (the operator is local); (2) row-band decomposition is bit-equal;
