@@ -64,7 +64,7 @@ struct alignas(128) TcSmem {
     __half B[4][64 * 16];            // Tz as UMMA K-major no-swizzle operands: [0] Bh, [1] Bl, [2]/[3] the K-swapped copies
     float2 L[2][4][LWP];             // luma of two groups: [buffer][row pair][column], .x = even row
     uint8_t Raw[3][8 * RawGeom<3>::ROW];
-    uint64_t bar_a_full, bar_a_free, bar_a_free_lo, bar_d_full[2];
+    uint64_t bar_a_free, bar_a_free_lo, bar_d_full[2];
     uint32_t tmem_base;
     int work;
 };
@@ -119,7 +119,13 @@ __device__ __forceinline__ bool elect_one()
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// Named barriers: 2,3 accumulator tiles; 4 converter threads; 5,6 luma buffer full; 7,8 luma buffer free.
+// Named barriers: 2,3 accumulator tiles; 4 converter threads; 5,6 luma buffer full; 7,8 luma buffer free; 9 step started
+// (MMA warp -> consumers: they block here instead of polling bar_d_full during the producers' phase); 10 operands of a
+// group stored (producers -> MMA warp).  A blocked bar.sync costs no issue slots, unlike an mbarrier poll loop.
+__device__ __forceinline__ void bar_step_arrive() { asm volatile("bar.arrive 9, 160;" ::: "memory"); }
+__device__ __forceinline__ void bar_step_sync() { asm volatile("bar.sync 9, 160;" ::: "memory"); }
+__device__ __forceinline__ void bar_afull_arrive() { asm volatile("bar.arrive 10, 160;" ::: "memory"); }
+__device__ __forceinline__ void bar_afull_sync() { asm volatile("bar.sync 10, 160;" ::: "memory"); }
 __device__ __forceinline__ void bar_converters() { asm volatile("bar.sync 4, 96;" ::: "memory"); }
 __device__ __forceinline__ void bar_lfull_arrive(int b) { asm volatile("bar.arrive %0, 224;" ::"r"(5 + b) : "memory"); }
 __device__ __forceinline__ void bar_lfull_sync(int b) { asm volatile("bar.sync %0, 224;" ::"r"(5 + b) : "memory"); }
@@ -306,7 +312,7 @@ __device__ __forceinline__ void split_pair(float2 x, uint32_t& hi, uint32_t& nlo
     nlo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// x-pass + split + tcgen05.st of group g (rows staged in s.L) into ring slot g&1; arrives on bar_a_full
+// x-pass + split + tcgen05.st of group g (rows staged in s.L) into ring slot g&1; arrives on the "operands stored" barrier
 __device__ __forceinline__ void produce_group(TcSmem& s, int g, int tid, uint32_t tmem_lane, long long* g_tt_acc)
 {
     (void) g_tt_acc;
@@ -347,10 +353,10 @@ __device__ __forceinline__ void produce_group(TcSmem& s, int g, int tid, uint32_
         TT_ACC(0, 2);
     }
     tc_fence_before();
-    __syncwarp();
-    // Group 0 is not announced on its own: the arrival of group 1 covers both (same warp, program order), so the MMA
-    // warp needs exactly one parity wait per step and can never be two phases behind the producers.
-    if (g >= 1 && (tid & 31) == 0) mbar_arrive(smem_u32(&s.bar_a_full));   // one arrival per producer warp
+    // Group 0 is not announced on its own: the arrival of group 1 covers both (same warp, program order).  The arrival
+    // of group g+1 needs the completion of MMA step g-1, which the MMA warp issues after its sync for step g-1: there
+    // is never more than one pending arrival.
+    if (g >= 1) bar_afull_arrive();
 }
 
 // ---- consumer fold -------------------------------------------------------------------------------------------
@@ -475,13 +481,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         if (tid == 0) {
             s.work = atomicAdd(counter, 1);
             if (!first) {
-                mbar_inval(smem_u32(&s.bar_a_full));
                 mbar_inval(smem_u32(&s.bar_a_free));
                 mbar_inval(smem_u32(&s.bar_a_free_lo));
                 mbar_inval(smem_u32(&s.bar_d_full[0]));
                 mbar_inval(smem_u32(&s.bar_d_full[1]));
             }
-            mbar_init(smem_u32(&s.bar_a_full), 4);
             mbar_init(smem_u32(&s.bar_a_free), 1);
             mbar_init(smem_u32(&s.bar_a_free_lo), 1);
             mbar_init(smem_u32(&s.bar_d_full[0]), 1);
@@ -540,6 +544,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         for (int st = 0; st < nsteps; st++) {
             TcFold<UNIFORM> f;
             f.init();
+            bar_step_sync();                                  // the MMA warp has started this step
             consume_k1<0, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
             consume_k1<1, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
             consume_k1<2, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
@@ -574,10 +579,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         for (int st = 0; st < nsteps; st++) {
             {
                 TT_T0();
-                mbar_wait(smem_u32(&s.bar_a_full), (uint32_t) (st & 1));     // groups st and st+1 are in TMEM
+                bar_afull_sync();                             // groups st and st+1 are in TMEM
                 TT_ACC(2, 0);
             }
             tc_fence_after();
+            bar_step_arrive();                                // wakes the consumers of this step
             // each operand copy is 2048 bytes = 128 descriptor address units
             const uint64_t bh = bd0 + (uint64_t) ((st & 1) ? 256 : 0);
             const uint64_t bl = bh + 128;
