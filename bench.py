@@ -38,6 +38,25 @@ WORKLOADS = {
 }
 
 
+def kernel_name(blocksize, kernel):
+    if blocksize == 8:
+        return {0: "dctc_k1_tc8_kernel (tcgen05 y-pass)", 3: "dctc_k1_tc8_kernel (tcgen05 y-pass)",
+                2: "dctc_k1_march8_kernel (FP32x2 register march)"}.get(kernel, "dctc_k1_tile_kernel (FP32)")
+    if blocksize in (2, 4) and kernel == 0:
+        return "dctc_k1_small_kernel (FP32 streaming register march)"
+    return "dctc_k1_tile_kernel (FP32)"
+
+
+def kernel_note(blocksize):
+    base = "traffic = DRAM bytes per launch from ncu (profiles/traffic.json); "
+    if blocksize == 8:
+        return base + ("blocksize 8 is compute-bound (24 tcgen05 MMAs + 32 FMNMX3 per 8x128 px), not HBM-bound: "
+                       "see DESIGN.md section 4")
+    if blocksize in (2, 4):
+        return base + "blocksize %d: HBM / instruction-issue bound streaming kernel, see DESIGN.md section 4" % blocksize
+    return base + "blocksize 16 runs in the FP32 tile kernel (FP32-pipe bound)"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -259,9 +278,7 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_kind": "of " + peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel": "dctc_k1_tc8_kernel (tcgen05 y-pass)" if (args.blocksize == 8 and args.kernel in (0, 3)) else "dctc_k1 (FP32)",
-                "note": "traffic = DRAM bytes per launch from ncu (profiles/traffic.json); blocksize 8 is compute-bound "
-                        "(24 tcgen05 MMAs + 32 FMNMX3 per 8x128 px), not HBM-bound: see DESIGN.md section 4"}
+                "kernel": kernel_name(args.blocksize, args.kernel), "note": kernel_note(args.blocksize)}
 
     # e2e: the same metric through the host-buffer C-ABI call, pinned host memory, copies inside the timed region
     e2e = None
@@ -300,7 +317,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.workload == "gigapixel" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict({"workload": wl["desc"], "blocksize": args.blocksize, "edges": 0.5, "textures": 0.5,
+            "config": dict({"workload": wl["desc"].replace("blocksize 8", "blocksize %d" % args.blocksize), "blocksize": args.blocksize, "edges": 0.5, "textures": 0.5,
                             "kernel": args.kernel, "l2": "inputs+outputs per step exceed L2 (distinct frames)",
                             "parallelism": "frames sharded, no collective" if args.workload != "gigapixel" else "row bands"},
                            **cfg_extra),
