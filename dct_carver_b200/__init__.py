@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "dctc_version", "dctc_device_count", "dctc_stream", "dctc_launch_count",
     "dctc_energy_full", "dctc_energy_full_dev", "dctc_energy_batch_dev", "dctc_energy_band_dev", "dctc_energy_batch",
     "dctc_carver_load", "dctc_carver_width", "dctc_carver_height", "dctc_carver_energy", "dctc_carve_and_update",
-    "dctc_carver_image", "dctc_carver_resize_width", "dctc_pixel_energy",
+    "dctc_carver_image", "dctc_carver_resize_width", "dctc_carver_set_incremental", "dctc_carver_rebuild_count", "dctc_pixel_energy",
     "dctc_energy_minmax_dev", "dctc_energy_image_dev", "dctc_carver_energy_image", "dctc_preview_energy",
     "dctc_carver_set_dump_vmaps", "dctc_carver_vmap", "dctc_carver_paint_seams",
     "dctc_synth_fill_dev", "dctc_synth_byte", "dctc_ipc_export", "dctc_ipc_open", "dctc_ipc_close",
@@ -89,6 +89,8 @@ def lib():
         "dctc_carve_and_update": (i32, [vp, vp, vp, vp, vp]),
         "dctc_carver_image": (i32, [vp, vp]),
         "dctc_carver_resize_width": (i32, [vp, i32, vp]),
+        "dctc_carver_rebuild_count": (i32, [vp]),
+        "dctc_carver_set_incremental": (i32, [vp, i32]),
         "dctc_energy_minmax_dev": (i32, [vp, vp, C.c_size_t, i32, i32, vp]),
         "dctc_energy_image_dev": (i32, [vp, vp, C.c_size_t, i32, i32, vp, vp, C.c_size_t, i32]),
         "dctc_carver_energy_image": (i32, [vp, vp]),
@@ -297,6 +299,15 @@ class Context:
         _check(lib().dctc_carver_resize_width(self._h, int(n_seams), _ptr(seams) if n_seams else None),
                "dctc_carver_resize_width")
         return seams
+
+    def carver_set_incremental(self, on):
+        """Device seam loop: update the cumulative map incrementally (liblqr's update_mmap) instead of rebuilding it."""
+        _check(lib().dctc_carver_set_incremental(self._h, int(bool(on))), "dctc_carver_set_incremental")
+
+    def carver_rebuild_count(self):
+        """Full cumulative-map rebuilds the device seam loop needed since carver_load (the other seams were served by
+        the incremental update)."""
+        return int(lib().dctc_carver_rebuild_count(self._h))
 
     def preview_energy(self, img, want_image=True):
         """Preview-path operator (dct_energy_preview, src/render.c:421-501): returns (energy float map, normalised

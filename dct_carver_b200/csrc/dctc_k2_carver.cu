@@ -24,12 +24,31 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
 template <int NT, int K>
 __global__ void __launch_bounds__(NT) dctc_carve_rows_kernel(uint8_t* __restrict__ img, size_t pitch, int channels,
                                                              float* __restrict__ en, size_t en_pitch,
-                                                             const int* __restrict__ seam, int w_old)
+                                                             const int* __restrict__ seam, int w_old,
+                                                             float* __restrict__ mplane, size_t m_pitch)
 {
     const int y = blockIdx.x;
     const int s = seam[y];
     uint8_t* row = img + (size_t) y * pitch;
     float* erow = en + (size_t) y * en_pitch;
+    // cumulative map of the seam DP (liblqr keeps it per pixel, so it moves with the pixels): dst x in [s, w_old-1)
+    if (mplane) {
+        float* mrow = mplane + (size_t) y * m_pitch;
+        for (int base = s; base < w_old - 1; base += NT * K) {
+            float v[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int x = base + k * NT + threadIdx.x;
+                v[k] = x < w_old - 1 ? mrow[x + 1] : 0.0f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int x = base + k * NT + threadIdx.x;
+                if (x < w_old - 1) mrow[x] = v[k];
+            }
+        }
+    }
     // energy floats: dst x in [s, w_old-1)
     for (int base = s; base < w_old - 1; base += NT * K) {
         float v[K];
@@ -120,8 +139,12 @@ __device__ __forceinline__ void dp_st_cluster_s32(uint32_t ra, int v) { asm vola
 template <int DP_P>               // float4 groups per lane: strip = 128 * DP_P columns, 128 * DP_P - 32 of them published
 __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dctc_seam_dp_kernel(const float* __restrict__ en, size_t en_pitch, int w, int h,
                                                                     float* __restrict__ mplane, size_t m_pitch,
-                                                                    int* __restrict__ seam, int* __restrict__ seam_log)
+                                                                    int* __restrict__ seam, int* __restrict__ seam_log,
+                                                                    int* __restrict__ run_flag)
 {
+    // fallback of the incremental update (dctc_seam_incr_kernel): runs only when that kernel asked for a rebuild
+    if (run_flag && *run_flag == 0) return;       // uniform over the cluster, before any cluster barrier
+    if (run_flag && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(run_flag + 1, 1);   // rebuilds since the session was loaded
     constexpr int CPL = 4 * DP_P;                 // cells per lane
     constexpr int STRIP = 32 * CPL;               // columns a warp computes
     constexpr int WOUT = STRIP - 2 * DP_R;        // columns a warp publishes
@@ -328,6 +351,256 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     }
 }
 
+// ---- incremental cumulative map (liblqr's update_mmap) -----------------------------------------------------------
+// After a seam is removed only part of the cumulative map changes: the cells inside the energy band of the removed seam
+// (their energy, or the identity of their parents, changed) and, row after row, the cells below a cell whose value
+// changed.  liblqr's update_mmap walks the rows with exactly that shrinking / growing column range instead of
+// rebuilding the map (lqr_carver_resize, src/render.c:377).  Here one warp does the walk: the cumulative plane was
+// compacted over the seam by the carve kernel, row y is recomputed for x in
+//     R(y) = band(y)  U  [first changed cell of row y-1  - 1,  last changed cell of row y-1  + 1]
+// with the same FP32 formula as the full rebuild, so the plane (and every later seam) is bit-identical to it.
+// R(y) grows by at most one column per side and row, so the energies and old map values a row can need are known
+// INCR_D rows ahead: they are staged with cp.async into a shared-memory ring, and the walk itself touches shared memory
+// only (lane l owns the columns lo + l + 32k; the recomputed row is handed to the next one through a double buffer with
+// two unchanged cells on each side).  R(y) wider than INCR_CAP columns raises the rebuild flag and the full DP kernel
+// takes over for this seam.  The walk ends with the leftmost minimum of the last row and the same back-track as the
+// full kernel.
+// MEASURED (1920x1080 noise, 480 seams): the walk recomputes ~150 columns per row on average and needs the full rebuild
+// for 2 of 480 seams, but ONE warp spends ~900 clk per row on it (phases per row: 250-470 clk row arithmetic, ~180 clk
+// side cells + next range, ~340 clk staging; a lone warp has no other warp to hide its 4-6 clk dependent-issue
+// latencies behind), i.e. 918 us per seam against 430 us for the cluster-wide rebuild.  It is therefore OFF by default
+// (dctc_carver_set_incremental) and kept as the bit-identical reference point for a multi-warp block version.
+#ifndef DCTC_INCR_ABL
+#define DCTC_INCR_ABL 0   // timing ablations only
+#endif
+constexpr int INCR_CAP = 512;                           // widest recomputed range per row
+constexpr int INCR_D = 8;                               // rows staged ahead
+constexpr int INCR_T = 8;                               // rows between two tightenings of the recomputed range
+constexpr int INCR_SW = INCR_CAP + 2 * INCR_D + 16;     // floats per staged row and plane
+
+// one row of the walk with NK columns per lane: every shared-memory load first, then the arithmetic and the stores
+template <int NK>
+__device__ __forceinline__ void incr_row(int y, int lane, int lo, int hi, int w, int plo, const float* __restrict__ re,
+                                         const float* __restrict__ rm, int xs, const float* __restrict__ prev,
+                                         float* __restrict__ next, float* __restrict__ mrow, int& clo, int& chi)
+{
+    const float INF = __int_as_float(0x7f800000);
+    float e[NK], mo[NK], pl[NK], pc[NK], pr[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        const int xc = min(lo + lane + 32 * k, hi);
+        e[k] = re[xc - xs];
+        mo[k] = rm[xc - xs];
+        const int i = y > 0 ? xc - plo + 2 : 1;
+        pl[k] = prev[i - 1];
+        pc[k] = prev[i];
+        pr[k] = prev[i + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        const int x = lo + lane + 32 * k;
+        if (x <= hi) {
+            float mn = e[k];
+            if (y > 0) mn = e[k] + fminf(fminf(x > 0 ? pl[k] : INF, pc[k]), x < w - 1 ? pr[k] : INF);
+            next[x - lo + 2] = mn;
+            if (__float_as_uint(mn) != __float_as_uint(mo[k])) {
+#if DCTC_INCR_ABL != 1
+                mrow[x] = mn;
+#endif
+                clo = min(clo, x);
+                chi = max(chi, x);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) dctc_seam_incr_kernel(const float* __restrict__ en, size_t en_pitch, int w, int h,
+                                                            float* __restrict__ mplane, size_t m_pitch, int r,
+                                                            int* __restrict__ seam, int* __restrict__ seam_log,
+                                                            int* __restrict__ rebuild_flag)
+{
+    extern __shared__ __align__(16) int incr_sm[];
+    float* ring = reinterpret_cast<float*>(incr_sm);                       // INCR_D slots x (energy row, map row) x INCR_SW
+    float* buf = ring + INCR_D * 2 * INCR_SW;                              // two hand-over rows of INCR_CAP + 4 cells
+    int* xsb = reinterpret_cast<int*>(buf + 2 * (INCR_CAP + 4));           // first staged column per slot
+    int* bmin = xsb + INCR_D;                                              // band of the removed seam per row
+    int* bmax = bmin + h;
+    __shared__ __align__(16) float win[32][DP_WIN];
+    const int lane = threadIdx.x;
+    const float INF = __int_as_float(0x7f800000);
+    if (lane == 0) *rebuild_flag = 0;
+    for (int y = lane; y < h; y += 32) {
+        int lo, hi;
+        dctc_band_limits(seam, y, h, w, r, &lo, &hi);
+        bmin[y] = lo;
+        bmax[y] = hi;
+    }
+    __syncwarp();
+    const int xmax4 = ((w + 3) & ~3) - 1;             // last column of the 16-byte chunk that holds column w-1
+    // stage row ys (columns that R(ys) and its two neighbours on each side can reach from the range [lo, hi] of a row
+    // at most INCR_D above it) into ring slot ys % INCR_D
+    auto stage = [&](int ys, int lo, int hi) {
+        if (ys < h) {
+            const int slot = ys % INCR_D;
+            const int s0 = max(0, lo - INCR_D - 2) & ~3, s1 = min(xmax4, (hi + INCR_D + 2) | 3);
+            if (lane == 0) xsb[slot] = s0;
+            const float* ge = en + (size_t) ys * en_pitch + s0;
+            const float* gm = mplane + (size_t) ys * m_pitch + s0;
+            float* de = ring + slot * 2 * INCR_SW;
+            float* dm = de + INCR_SW;
+            const int nch = (s1 - s0 + 1) >> 2;
+            for (int c = lane; c < nch; c += 32) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(de + 4 * c)), "l"(ge + 4 * c) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(dm + 4 * c)), "l"(gm + 4 * c) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int lo = bmin[0], hi = bmax[0];
+    if (hi - lo + 1 > INCR_CAP) {
+        if (lane == 0) *rebuild_flag = 1;
+        return;
+    }
+    for (int ys = 0; ys < INCR_D; ys++) stage(ys, lo, hi);
+    float* prev = buf;
+    float* next = buf + INCR_CAP + 4;
+    int plo = 0;                                      // prev[i] holds the cell x = plo - 2 + i of row y-1
+#ifdef DCTC_INCR_STATS
+    int stat_w = 0;
+    long long st[5] = {0, 0, 0, 0, 0};
+    const long long stat_t0 = clock64();
+#endif
+    for (int y = 0; y < h; y++) {
+        const int width = hi - lo + 1;
+#ifdef DCTC_INCR_STATS
+        stat_w += width;
+#endif
+        if (width > INCR_CAP) {                       // uniform
+            if (lane == 0) *rebuild_flag = 1;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            return;
+        }
+#ifdef DCTC_INCR_STATS
+        const long long c0 = clock64();
+#endif
+        asm volatile("cp.async.wait_group %0;" ::"n"(INCR_D - 1) : "memory");   // row y has landed (own copies)
+        __syncwarp();                                                            // ... and everybody's
+#ifdef DCTC_INCR_STATS
+        const long long c1 = clock64();
+#endif
+        const int slot = y % INCR_D;
+        const float* re = ring + slot * 2 * INCR_SW;
+        const float* rm = re + INCR_SW;
+        const int xs = xsb[slot];
+        float* mrow = mplane + (size_t) y * m_pitch;
+        int clo = 0x7fffffff, chi = -1;
+        if (width <= 32) incr_row<1>(y, lane, lo, hi, w, plo, re, rm, xs, prev, next, mrow, clo, chi);
+        else if (width <= 64) incr_row<2>(y, lane, lo, hi, w, plo, re, rm, xs, prev, next, mrow, clo, chi);
+        else if (width <= 128) incr_row<4>(y, lane, lo, hi, w, plo, re, rm, xs, prev, next, mrow, clo, chi);
+        else if (width <= 256) incr_row<8>(y, lane, lo, hi, w, plo, re, rm, xs, prev, next, mrow, clo, chi);
+        else incr_row<16>(y, lane, lo, hi, w, plo, re, rm, xs, prev, next, mrow, clo, chi);
+#ifdef DCTC_INCR_STATS
+        const long long c2 = clock64();
+#endif
+        if (lane < 4) {   // two unchanged cells on each side of the range, from the staged (old) map row
+            const int xe = lane < 2 ? lo - 2 + lane : hi + lane - 1;
+            const int idx = lane < 2 ? lane : width + lane;
+            next[idx] = (xe >= 0 && xe < w) ? rm[xe - xs] : INF;
+        }
+        // Next range.  Finding the changed cells is a warp-wide reduction on the row-to-row critical path, so it is done
+        // only every INCR_T rows; in between the range simply grows by one column per side (a superset of R(y+1):
+        // cells recomputed without need come out bit-identical, and band(y+1) lies inside band(y) +- 1).
+        int nlo = max(lo - 1, 0), nhi = min(hi + 1, w - 1);
+        if ((y & (INCR_T - 1)) == INCR_T - 1 && y + 1 < h) {
+            clo = __reduce_min_sync(0xffffffffu, clo);
+            chi = __reduce_max_sync(0xffffffffu, chi);
+            nlo = bmin[y + 1];
+            nhi = bmax[y + 1];
+            if (chi >= 0) { nlo = min(nlo, clo - 1); nhi = max(nhi, chi + 1); }
+            nlo = max(nlo, 0);
+            nhi = min(nhi, w - 1);
+        }
+        plo = lo;
+        float* t = prev; prev = next; next = t;
+        lo = nlo;
+        hi = nhi;
+#ifdef DCTC_INCR_STATS
+        const long long c3 = clock64();
+#endif
+        __syncwarp();                                 // hand-over row written, ring slot of row y read by everybody
+#ifdef DCTC_INCR_STATS
+        const long long c4 = clock64();
+#endif
+#if DCTC_INCR_ABL == 2
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+        if (hi - lo + 1 <= INCR_CAP) stage(y + INCR_D, lo, hi);                  // refills the slot row y sat in
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+#ifdef DCTC_INCR_STATS
+        st[0] += c1 - c0; st[1] += c2 - c1; st[2] += c3 - c2; st[3] += c4 - c3; st[4] += clock64() - c4;
+#endif
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef DCTC_INCR_STATS
+    if (lane == 0) { atomicAdd(rebuild_flag + 2, stat_w / 16); atomicAdd(rebuild_flag + 3, (int) ((clock64() - stat_t0) >> 10));
+        if (w == 1900) printf("walk phases (clk per row): wait %lld, row %lld, ext+range %lld, syncwarp %lld, stage %lld\n", st[0] / h, st[1] / h, st[2] / h, st[3] / h, st[4] / h); }
+#endif
+    __threadfence();
+    __syncwarp();
+    // leftmost minimum of the last row (from L2: part of it was just rewritten)
+    const float* last = mplane + (size_t) (h - 1) * m_pitch;
+    float bv = INF;
+    int bi = 0x7fffffff;
+    for (int x = lane; x < w; x += 32) {
+        const float v = __ldcg(last + x);
+        if (v < bv || bi == 0x7fffffff) { bv = v; bi = x; }     // ascending x per lane: strict < keeps the leftmost
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    // back-track: same walk as in dctc_seam_dp_kernel (every lane follows the same path, lane 0 records it)
+    int x = bi;
+    if (lane == 0) { seam[h - 1] = x; if (seam_log) seam_log[h - 1] = x; }
+    const int max_base = (int) m_pitch - DP_WIN;
+    for (int ytop = h - 1; ytop >= 1; ytop -= 32) {
+        int base = (x - 36) & ~3;
+        base = base < 0 ? 0 : (base > max_base ? max_base : base);
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            float4 t[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int yy = ytop - 1 - (16 * hh + i);
+                t[i] = (yy >= 0 && lane < DP_WIN / 4) ? __ldcg(reinterpret_cast<const float4*>(mplane + (size_t) yy * m_pitch + base) + lane)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (lane < DP_WIN / 4) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) reinterpret_cast<float4*>(win[16 * hh + i])[lane] = t[i];
+            }
+        }
+        __syncwarp();
+        const int steps = ytop < 32 ? ytop : 32;
+        for (int i = 0; i < steps; i++) {
+            const float* wr = win[i] - base;
+            const float a = x > 0 ? wr[x - 1] : INF;
+            const float b = wr[x];
+            const float c = x < w - 1 ? wr[x + 1] : INF;
+            int arg = x - 1;
+            float best = a;
+            if (b < best) { best = b; arg = x; }
+            if (c < best) arg = x + 1;
+            x = arg;
+            if (lane == 0) { seam[ytop - 1 - i] = x; if (seam_log) seam_log[ytop - 1 - i] = x; }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- visibility map + seam display ---------------------------------------------------
 // liblqr's update_vsmap: the pixel removed from row y by the k-th seam is original column raw[y][s]; its entry of the
 // visibility map becomes k (1-based).  raw is compacted over the seam like the image (one CTA per row).
@@ -391,6 +664,7 @@ void dctc_carver_release(dctc_context* ctx)
     ctx->c_img = nullptr; ctx->c_en = nullptr; ctx->c_m = nullptr; ctx->c_dir = nullptr; ctx->c_seam_log = nullptr; ctx->c_seam_log_cap = 0; ctx->c_raw = nullptr; ctx->c_vs = nullptr; ctx->c_vs_depth = 0; ctx->c_seam = nullptr; ctx->c_band = nullptr;
     ctx->c_band_vals = nullptr; ctx->h_mirror = nullptr; ctx->h_band = nullptr;
     ctx->c_w0 = ctx->c_w = ctx->c_h = ctx->c_ch = 0;
+    ctx->c_m_valid = false;
     ctx->c_pitch = 0;
     ctx->c_en_pitch = 0;
     ctx->mirror_valid = false;
@@ -481,11 +755,12 @@ int dctc_carve_and_update(dctc_context* ctx, const int* seam_x, float* band_out,
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaMemcpyAsync(ctx->c_seam, h_seam, sizeof(int) * h, cudaMemcpyHostToDevice, ctx->stream));
     dctc_carve_rows_kernel<256, 4><<<h, 256, 0, ctx->stream>>>(ctx->c_img, ctx->c_pitch, ctx->c_ch, ctx->c_en,
-                                                               ctx->c_en_pitch, ctx->c_seam, w_old);
+                                                               ctx->c_en_pitch, ctx->c_seam, w_old, nullptr, 0);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     ctx->c_w = w_old - 1;
     ctx->mirror_valid = false;
+    ctx->c_m_valid = false;     // the host picked this seam: the device's cumulative plane no longer matches
     DctcK1Args a;
     carver_args(ctx, a);
     a.seam = ctx->c_seam; a.band_r = r; a.band_vals = ctx->c_band_vals; a.band_stride = bs;
@@ -552,11 +827,28 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     const size_t dp_smem = sizeof(float) * 2 * (size_t) wpc * wout;
     auto dp = P == 1 ? dctc_seam_dp_kernel<1> : P == 2 ? dctc_seam_dp_kernel<2> : dctc_seam_dp_kernel<4>;
     if (dp_smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dp_smem));
+    // incremental update (update_mmap): one warp; needs the band table of h rows twice in shared memory
+    const size_t incr_smem = sizeof(float) * (INCR_D * 2 * INCR_SW + 2 * (INCR_CAP + 4)) + sizeof(int) * (INCR_D + 2 * (size_t) h);
+    const bool incr_ok = ctx->c_incremental && incr_smem <= 160 * 1024;
+    if (incr_ok)   // dynamic + static shared memory can exceed the 48 KB default
+        CK(ctx, cudaFuncSetAttribute(dctc_seam_incr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) incr_smem));
+    if (!ctx->c_band) {
+        CK(ctx, cudaMalloc((void**) &ctx->c_band, sizeof(int) * 4));
+        CK(ctx, cudaMemsetAsync(ctx->c_band, 0, sizeof(int) * 4, ctx->stream));
+    }
     for (int s = 0; s < n_seams; s++) {
         const int w_old = ctx->c_w;
-        // build_mmap + build_vpath
-        dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam,
-                                         ctx->c_seam_log + (size_t) s * h);
+        int* log_s = ctx->c_seam_log + (size_t) s * h;
+        if (ctx->c_m_valid && incr_ok) {
+            // update_mmap + build_vpath: walk the changed cells only; the full rebuild below runs only if the walk gave up
+            dctc_seam_incr_kernel<<<1, 32, incr_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, r,
+                                                                     ctx->c_seam, log_s, ctx->c_band);
+            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, ctx->c_band);
+            ctx->launches++;
+        } else {
+            // build_mmap + build_vpath
+            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr);
+        }
 #ifdef DCTC_SYNC_DEBUG
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }
 #endif
@@ -566,10 +858,11 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         }
         // carve: compact image and energy rows over the seam
         dctc_carve_rows_kernel<256, 4><<<h, 256, 0, ctx->stream>>>(ctx->c_img, ctx->c_pitch, ctx->c_ch, ctx->c_en,
-                                                                   ctx->c_en_pitch, ctx->c_seam, w_old);
+                                                                   ctx->c_en_pitch, ctx->c_seam, w_old, incr_ok ? ctx->c_m : nullptr, m_pitch);
         CK(ctx, cudaGetLastError());
         ctx->launches += 2;
         ctx->c_w = w_old - 1;
+        ctx->c_m_valid = incr_ok;   // the plane now holds the map of the image before this removal, moved with the pixels
         // update_emap: K1 in band mode around the removed seam
         DctcK1Args a;
         carver_args(ctx, a);
@@ -588,6 +881,27 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         CK(ctx, cudaMemcpyAsync(seams_out, ctx->c_seam_log, sizeof(int) * (size_t) n_seams * h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return DCTC_OK;
+}
+
+int dctc_carver_set_incremental(dctc_context* ctx, int on)
+{
+    if (!ctx) return DCTC_ERR_INVALID;
+    ctx->c_incremental = on != 0;
+    return DCTC_OK;
+}
+
+int dctc_carver_rebuild_count(dctc_context* ctx)
+{
+    if (!ctx || !ctx->c_img) return -1;
+    if (!ctx->c_band) return 0;
+    int v[4] = {0, 0, 0, 0};
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(v, ctx->c_band, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+#ifdef DCTC_INCR_STATS
+    fprintf(stderr, "incremental map: rebuilds %d, sum of range widths / 16 = %d, walk kclk = %d\n", v[1], v[2], v[3]);
+#endif
+    return v[1];
 }
 
 int dctc_carver_set_dump_vmaps(dctc_context* ctx, int on)

@@ -52,7 +52,9 @@ struct dctc_context {
     int c_vs_depth = 0;
     bool c_dump_vmaps = false;
     int* c_seam = nullptr;         // h entries
-    int* c_band = nullptr;         // 2*h entries: xmin, xmax
+    int* c_band = nullptr;         // c_band[0]: 'rebuild the cumulative map from scratch' flag of the incremental seam DP (device)
+    bool c_incremental = false;    // device seam loop: update the cumulative map incrementally (dctc_carver_set_incremental)
+    bool c_m_valid = false;        // the cumulative plane holds the map of the image before the last removal, compacted over that seam
     float* c_band_vals = nullptr;  // packed band values
     float* h_mirror = nullptr;     // host mirror of the energy map (pinned)
     int* h_band = nullptr;         // pinned 2*h

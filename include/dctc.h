@@ -142,6 +142,13 @@ int dctc_carver_image(dctc_context *ctx, uint8_t *out);
  * at the time of removal.  Mirrors lqr_carver_resize(carver, w - n_seams, h) (src/render.c:377) with
  * delta_x = 1, rigidity = 0 (src/render.c:313). */
 int dctc_carver_resize_width(dctc_context *ctx, int n_seams, int *seams_out);
+/* Optional: let the device loop update its cumulative map incrementally after each seam, like liblqr's update_mmap
+ * (only the cells the removed seam can have changed are recomputed; a row whose changed range gets too wide falls
+ * back to the full rebuild).  Same seams bit for bit; off by default because the full rebuild on an 8-CTA cluster is
+ * currently the faster of the two. */
+int dctc_carver_set_incremental(dctc_context *ctx, int on);
+/* Number of full cumulative-map rebuilds the incremental mode fell back to since dctc_carver_load (-1 on error). */
+int dctc_carver_rebuild_count(dctc_context *ctx);
 
 /* ---- visibility map and seam display ------------------------------------------------------------------------
  * lqr_carver_set_dump_vmaps (src/render.c:374): ask the session to record, for every ORIGINAL pixel, the order in

@@ -164,6 +164,33 @@ def test_device_seam_loop_equals_host_carver(ctx, b, ch, w, h, n):
     assert np.array_equal(ctx.carver_energy(), ctx.energy_full(want["image"]))
 
 
+@pytest.mark.parametrize("b,ch,w,h,n,pattern", [(8, 3, 150, 90, 25, 0), (8, 1, 97, 75, 40, 0), (4, 3, 64, 33, 10, 0),
+                                                (8, 3, 1100, 40, 30, 0), (8, 3, 40, 300, 8, 0), (2, 1, 9, 1, 3, 0),
+                                                (8, 3, 700, 200, 30, 3), (8, 3, 640, 120, 12, 1), (8, 3, 64, 48, 6, 2)])
+def test_device_seam_loop_incremental_map_equals_rebuild(ctx, b, ch, w, h, n, pattern):
+    """Optional incremental cumulative map (liblqr's update_mmap on the device, dctc_carver_set_incremental): same
+    seams, image and energy plane, bit for bit, as the default loop that rebuilds the map for every seam -- including
+    images full of ties (gradient / checkerboard patterns), ranges that hit the image borders and the fall-back to a
+    full rebuild when a row's changed range gets too wide."""
+    img = ol.synth_image(w, h, ch, 700 + w, pattern)
+    ctx.set_params(b, 0.5, 0.5)
+    ctx.carver_load(img)
+    want = ctx.carver_resize_width(n)
+    want_img, want_en = ctx.carver_image(), ctx.carver_energy()
+    ctx.carver_load(img)
+    ctx.carver_set_incremental(True)
+    try:
+        # two calls: the second one continues incrementally from the map the first one left behind
+        got = np.concatenate([ctx.carver_resize_width(n // 2), ctx.carver_resize_width(n - n // 2)])
+        rebuilds = ctx.carver_rebuild_count()
+    finally:
+        ctx.carver_set_incremental(False)
+    assert np.array_equal(got, want)
+    assert np.array_equal(ctx.carver_image(), want_img)
+    assert np.array_equal(ctx.carver_energy(), want_en)
+    assert 0 <= rebuilds < n
+
+
 def test_device_seam_loop_ties_and_flat_image(ctx):
     """Constant image: every energy is 0, every cumulative value ties; liblqr's rule then removes column 0 in every
     row, every time (leftmost minimum, first strict minimum among parents)."""
