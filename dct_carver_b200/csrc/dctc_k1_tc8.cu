@@ -269,33 +269,53 @@ __device__ __forceinline__ void dct8_fwd2_scaled(const float2* __restrict__ v, f
 }
 
 // raw rows -> luma row pairs; staged index i <-> image column clamp(x0 - 4 + i) (src/render.c:122-132).
-// A task is one 4-pixel group of one row pair; groups that touch the image border take the per-pixel clamped path.
+// A task is one 4-pixel group of one row pair (4 x 34 tasks per group of rows); a converter thread owns the same one or
+// two tasks for every group of an item, so their offsets and the border test are computed once per item (ConvMap).
+// Groups that touch the image border take the per-pixel clamped path.
 template <int CH>
-__device__ __forceinline__ void convert_raw(const DctcK1Args& a, const uint8_t* __restrict__ R, float2 (*L)[LWP], int x0, int ct)
-{
-    constexpr int ROW = RawGeom<CH>::ROW;
-    for (int task = ct; task < 4 * NQUAD; task += NCONV) {
-        const int p = task / NQUAD, q = task - p * NQUAD - 1;       // row pair 0..3, quad -1..32
-        const int gx = x0 + 4 * q;
-        const uint8_t* r0 = R + (2 * p) * ROW + 16 + 4 * CH * q;
-        const uint8_t* r1 = r0 + ROW;
-        float l0[4], l1[4];
-        if (gx >= 0 && gx + 3 < a.w) {
-            quad_luma<CH>(r0, l0);
-            quad_luma<CH>(r1, l1);
-        } else {
+struct ConvMap {
+    static constexpr int ROW = RawGeom<CH>::ROW;
+    static constexpr int PER = (4 * NQUAD + NCONV - 1) / NCONV;   // 2
+    int roff[PER];     // byte offset of the task's first raw row inside a raw buffer, -1: no task
+    int loff[PER];     // float2 index inside a luma buffer
+    int gx[PER];       // image column of the first pixel; INT_MIN when the four pixels are all inside the image
+    __device__ __forceinline__ void init(const DctcK1Args& a, int x0, int ct)
+    {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int off = (max(0, min(gx + i, a.w - 1)) - gx) * CH;
-                l0[i] = luma_raw<CH>(r0 + off);
-                l1[i] = luma_raw<CH>(r1 + off);
-            }
+        for (int i = 0; i < PER; i++) {
+            const int task = ct + i * NCONV;
+            const int p = task / NQUAD, q = task - p * NQUAD - 1;   // row pair 0..3, quad -1..32
+            const int g = x0 + 4 * q;
+            roff[i] = task < 4 * NQUAD ? (2 * p) * ROW + 16 + 4 * CH * q : -1;
+            loff[i] = p * LWP + 4 * q + 4;
+            gx[i] = (g >= 0 && g + 3 < a.w) ? (int) 0x80000000 : g;
         }
-        float4* dst = reinterpret_cast<float4*>(&L[p][4 * q + 4]);
-        dst[0] = make_float4(l0[0], l1[0], l0[1], l1[1]);
-        dst[1] = make_float4(l0[2], l1[2], l0[3], l1[3]);
     }
-}
+    __device__ __forceinline__ void convert(const DctcK1Args& a, const uint8_t* __restrict__ R, float2* __restrict__ L) const
+    {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            if (roff[i] < 0) continue;
+            const uint8_t* r0 = R + roff[i];
+            const uint8_t* r1 = r0 + ROW;
+            float l0[4], l1[4];
+            if (gx[i] == (int) 0x80000000) {
+                quad_luma<CH>(r0, l0);
+                quad_luma<CH>(r1, l1);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int off = (max(0, min(gx[i] + k, a.w - 1)) - gx[i]) * CH;
+                    l0[k] = luma_raw<CH>(r0 + off);
+                    l1[k] = luma_raw<CH>(r1 + off);
+                }
+            }
+            float4* dst = reinterpret_cast<float4*>(L + loff[i]);
+            dst[0] = make_float4(l0[0], l1[0], l0[1], l1[1]);
+            dst[1] = make_float4(l0[2], l1[2], l0[3], l1[3]);
+        }
+    }
+};
 
 // H -> fp16 hi and fp16 MINUS lo for two vertically adjacent rows (low half = even row = even K index).
 // hi = rn16(H); the residual comes from one mixed-precision subtract per value (sub.f32.f16 = FHADD: hi - H, exact),
@@ -622,6 +642,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         const int ct = tid - (NTHREADS - NCONV);
         StageMap<CH> sm;
         sm.init(a, x0, ct);
+        ConvMap<CH> cm;
+        cm.init(a, x0, ct);
         sm.stage(a, img, s.Raw[0], y0 - 3);
         sm.stage(a, img, s.Raw[1], y0 + 5);
         int slot = 0;                                         // raw buffer of group g (g % 3)
@@ -641,7 +663,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
                 bar_lfree_sync(g & 1);                        // the producers have read group g-2 out of this buffer
                 TT_ACC(3, 2);
             }
-            convert_raw<CH>(a, s.Raw[slot], s.L[g & 1], x0, ct);
+            cm.convert(a, s.Raw[slot], &s.L[g & 1][0][0]);
             bar_lfull_arrive(g & 1);
             const int nslot = slot == 0 ? 2 : slot - 1;       // (g + 2) % 3
             if (g + 2 <= nsteps) sm.stage(a, img, s.Raw[nslot], y0 - 3 + 8 * (g + 2));
