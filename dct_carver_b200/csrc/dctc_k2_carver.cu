@@ -6,6 +6,7 @@
 // energy plane stay resident in HBM; one kernel compacts both over the seam, then the K1 tile kernel runs in band
 // mode over just the touched pixels, with arithmetic identical to a full recompute (bit-identical results).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "dctc_common.cuh"
 #include "dctc_launch.h"
@@ -136,7 +137,32 @@ __device__ __forceinline__ float4 dp_ld_cluster_v4(uint32_t ra)
 __device__ __forceinline__ void dp_st_cluster_f32(uint32_t ra, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory"); }
 __device__ __forceinline__ void dp_st_cluster_s32(uint32_t ra, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(ra), "r"(v) : "memory"); }
 
-template <int DP_P>               // float4 groups per lane: strip = 128 * DP_P columns, 128 * DP_P - 32 of them published
+// TMA = true: the energies of a strip are staged DP_NST blocks of DP_R rows ahead into shared memory with 1-D bulk
+// async copies (cp.async.bulk, completion on an mbarrier per warp and stage) instead of a register ring of plain
+// loads: nothing the cluster barrier's memory fence has to wait for, and 48 rows in flight per warp.
+constexpr int DP_NST = 3;
+
+__device__ __forceinline__ uint32_t dp_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+// bounded parity wait: a protocol error traps after ~2^24 polls instead of hanging the GPU
+__device__ __forceinline__ void dp_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "DP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DP_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 0x1000000;\n"
+        "@p bra DP_WAIT;\n"
+        "trap;\n"
+        "DP_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <int DP_P, bool TMA>     // DP_P float4 groups per lane: strip = 128 * DP_P columns, 128 * DP_P - 32 of them published
 __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dctc_seam_dp_kernel(const float* __restrict__ en, size_t en_pitch, int w, int h,
                                                                     float* __restrict__ mplane, size_t m_pitch,
                                                                     int* __restrict__ seam, int* __restrict__ seam_log,
@@ -149,8 +175,10 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     constexpr int STRIP = 32 * CPL;               // columns a warp computes
     constexpr int WOUT = STRIP - 2 * DP_R;        // columns a warp publishes
     constexpr int HL = DP_R / CPL;                // halo lanes on each side (DP_R is a multiple of CPL)
-    constexpr int PF = 16 / DP_P;                 // energy rows in flight per lane (16 float4 registers)
-    extern __shared__ __align__(16) float xrow[]; // two exchange rows of (warps per CTA * WOUT) floats, double buffered
+    constexpr int PF = TMA ? 1 : 16 / DP_P;       // energy rows in flight per lane (register ring of the non-TMA variant)
+    extern __shared__ __align__(128) float xrow[]; // two exchange rows of (warps per CTA * WOUT) floats, double buffered;
+                                                  // TMA: followed by warps x DP_NST stages x DP_R rows x STRIP energies
+    __shared__ __align__(8) unsigned long long ebar[DP_MAXW][DP_NST];
     __shared__ float red_v[DP_CL * DP_MAXW];      // per-strip minima, gathered in CTA 0 through distributed shared memory
     __shared__ int red_i[DP_CL * DP_MAXW];
     __shared__ __align__(16) float win[32][DP_WIN];
@@ -190,6 +218,38 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     for (int g = 0; g < DP_P; g++) en_g[g] = en + (ld_ok[g] ? c0 + 4 * g : 0);
     const int hm1 = h - 1;
 
+    // TMA staging of this warp's strip: columns [cs, cs + STRIP) clipped to the row, DP_R rows per stage
+    const int cs = warp * WOUT - DP_R;
+    const int tx0 = max(cs, 0), tx1 = min(cs + STRIP, (int) en_pitch);
+    const int tbytes = tx1 > tx0 ? (tx1 - tx0) * 4 : 0;
+    float* estage = xrow + 2 * xlen + (size_t) (tid >> 5) * DP_NST * DP_R * STRIP;
+    const int nblocks = (h - 1 + DP_R - 1) / DP_R;
+    auto issue_block = [&](int blk) {       // rows 1 + blk * DP_R .. (clamped to h - 1) -> stage blk % DP_NST
+        const int st = blk % DP_NST;
+        const uint32_t bar = dp_smem_u32(&ebar[tid >> 5][st]);
+        if (lane == 0) {
+            if (tbytes > 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (tbytes * DP_R)) : "memory");
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+        __syncwarp();
+        if (lane < DP_R && tbytes > 0) {
+            const int y = min(1 + blk * DP_R + lane, hm1);
+            const float* src = en + (size_t) y * en_pitch + tx0;
+            const uint32_t dst = dp_smem_u32(estage + ((size_t) st * DP_R + lane) * STRIP + (tx0 - cs));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"((uint32_t) tbytes), "r"(bar) : "memory");
+        }
+    };
+    if (TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int st = 0; st < DP_NST; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&ebar[tid >> 5][st])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        for (int blk = 0; blk < DP_NST && blk < nblocks; blk++) issue_block(blk);
+    }
+
     float4 cur[DP_P], e[PF][DP_P];
 #pragma unroll
     for (int g = 0; g < DP_P; g++) {
@@ -197,21 +257,30 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
         const int x = c0 + 4 * g;
         if (central && ld_ok[g]) *reinterpret_cast<float4*>(mplane + x) = cur[g];
         patch(cur[g], inf_mask[g]);
+        if (!TMA) {
 #pragma unroll
-        for (int k = 0; k < PF; k++)               // e[k] holds row y with (y - 1) % PF == k
-            e[k][g] = __ldg(reinterpret_cast<const float4*>(en_g[g] + (size_t) min(1 + k, hm1) * en_pitch));
+            for (int k = 0; k < PF; k++)               // e[k] holds row y with (y - 1) % PF == k
+                e[k][g] = __ldg(reinterpret_cast<const float4*>(en_g[g] + (size_t) min(1 + k, hm1) * en_pitch));
+        }
     }
 #ifdef DCTC_SYNC_DEBUG
     const long long dbg_t0 = clock64();
 #endif
     float* mrow = mplane + m_pitch;
     int xb = 0;
-    for (int yb = 1; yb < h; yb += DP_R) {
+    int blk = 0;
+    for (int yb = 1; yb < h; yb += DP_R, blk++) {
+        const float* stg = estage + (size_t) (blk % DP_NST) * DP_R * STRIP + lane * CPL;
+        if (TMA) dp_mbar_wait(dp_smem_u32(&ebar[tid >> 5][blk % DP_NST]), (uint32_t) ((blk / DP_NST) & 1));
 #pragma unroll
         for (int kk = 0; kk < DP_R; kk++) {
             const int k = kk % PF;
             const int y = yb + kk;
             if (y < h) {                                                    // uniform across the CTA
+                if (TMA) {
+#pragma unroll
+                    for (int g = 0; g < DP_P; g++) e[0][g] = *reinterpret_cast<const float4*>(stg + kk * STRIP + 4 * g);
+                }
                 // neighbours across lanes; the strip's outermost lanes see +inf (their cells are never published)
                 float l = __shfl_up_sync(0xffffffffu, cur[DP_P - 1].w, 1);
                 float r = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
@@ -230,9 +299,11 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
                 // refill the ring slot just consumed with the row PF ahead (issued after the last use of the slot, so
                 // the load targets the slot's registers directly; they are not touched again for PF rows)
 #if !(DP_EXP & 1)
+                if (!TMA) {
 #pragma unroll
-                for (int g = 0; g < DP_P; g++)
-                    e[k][g] = __ldg(reinterpret_cast<const float4*>(en_g[g] + (size_t) min(y + PF, hm1) * en_pitch));
+                    for (int g = 0; g < DP_P; g++)
+                        e[k][g] = __ldg(reinterpret_cast<const float4*>(en_g[g] + (size_t) min(y + PF, hm1) * en_pitch));
+                }
 #endif
 #pragma unroll
                 for (int g = 0; g < DP_P; g++) {
@@ -244,6 +315,13 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
                     cur[g] = o[g];
                 }
                 mrow += m_pitch;
+            }
+        }
+        if (TMA) {                                   // this warp is done with the stage: refill it DP_NST blocks ahead
+            __syncwarp();
+            if (blk + DP_NST < nblocks) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_block(blk + DP_NST);
             }
         }
         // exchange the last row of the block: every warp publishes its central cells, then reloads its whole strip
@@ -824,9 +902,14 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     const int wout = 128 * P - 2 * DP_R;
     const int strips = (wcur + wout - 1) / wout;
     const int wpc = (strips + DP_CL - 1) / DP_CL;
-    const size_t dp_smem = sizeof(float) * 2 * (size_t) wpc * wout;
-    auto dp = P == 1 ? dctc_seam_dp_kernel<1> : P == 2 ? dctc_seam_dp_kernel<2> : dctc_seam_dp_kernel<4>;
-    if (dp_smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dp_smem));
+    // energies staged by bulk async copies when the DP_NST stages of every warp fit into shared memory
+    const size_t tma_smem = sizeof(float) * ((size_t) wpc * DP_NST * DP_R * 128 * P);
+    const bool tma = sizeof(float) * 2 * (size_t) wpc * wout + tma_smem <= 200 * 1024 && !getenv("DCTC_DP_NO_TMA");
+    const size_t dp_smem = sizeof(float) * 2 * (size_t) wpc * wout + (tma ? tma_smem : 0);
+    auto dp = P == 1 ? (tma ? dctc_seam_dp_kernel<1, true> : dctc_seam_dp_kernel<1, false>)
+            : P == 2 ? (tma ? dctc_seam_dp_kernel<2, true> : dctc_seam_dp_kernel<2, false>)
+                     : (tma ? dctc_seam_dp_kernel<4, true> : dctc_seam_dp_kernel<4, false>);
+    if (dp_smem > 40 * 1024) CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dp_smem));
     // incremental update (update_mmap): one warp; needs the band table of h rows twice in shared memory
     const size_t incr_smem = sizeof(float) * (INCR_D * 2 * INCR_SW + 2 * (INCR_CAP + 4)) + sizeof(int) * (INCR_D + 2 * (size_t) h);
     const bool incr_ok = ctx->c_incremental && incr_smem <= 160 * 1024;
