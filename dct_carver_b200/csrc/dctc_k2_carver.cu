@@ -98,14 +98,12 @@ __global__ void __launch_bounds__(NT) dctc_carve_rows_kernel(uint8_t* __restrict
 // garbage and the warp publishes only its central 128*P - 2*DP_R columns; every DP_R rows the warps exchange the
 // last row through shared memory (one barrier per DP_R rows) and restart with fresh halos.  Energies are
 // prefetched 8 rows ahead into registers; the cumulative rows go to a global float plane from which warp 0 re-derives
-// the parent choices during the back-track, in batches of 32 rows (the path moves at most one column per row, so the
-// 32 rows' 80-float windows around the current column are fetched with independent coalesced loads).
+// the parent choices during the back-track (dp_backtrack: 32-row batches through double-buffered shared-memory windows).
 // Cells outside the image hold +inf, which reproduces the range clipping.
 #ifndef DP_EXP
 #define DP_EXP 0   // timing experiments only
 #endif
 constexpr int DP_R = 16;          // rows between two exchanges = halo columns on each side of a strip
-constexpr int DP_WIN = 80;        // back-track window (floats)
 constexpr int DP_MAXW = 8;        // warps per CTA of the DP cluster (256 threads: room for a deep register prefetch ring)
 
 constexpr int DP_CL = 8;          // CTAs of the cluster the strips are spread over (a lone SM can only pull ~35 GB/s from L2:
@@ -136,6 +134,69 @@ __device__ __forceinline__ float4 dp_ld_cluster_v4(uint32_t ra)
 }
 __device__ __forceinline__ void dp_st_cluster_f32(uint32_t ra, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory"); }
 __device__ __forceinline__ void dp_st_cluster_s32(uint32_t ra, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(ra), "r"(v) : "memory"); }
+
+// ---- back-track (build_vpath) ------------------------------------------------------------------------------------
+// One warp walks up from the last row: parent of (y, x) = FIRST strict minimum of m[y-1][x-1], m[y-1][x], m[y-1][x+1].
+// Every lane follows the same path, lane 0 records it.  The cumulative rows are read in batches of 32 rows through
+// shared-memory windows of DP_WIN columns, double buffered: the path moves at most one column per row, so the window
+// of the NEXT batch (columns xs-66 .. xs+66 around the column xs at which the current batch starts) is known before
+// the current batch is walked, and its cp.async copies land while the walk (a chain of dependent shared-memory reads)
+// is running.
+constexpr int DP_WIN = 144;       // back-track window (floats); the cumulative plane's pitch is at least this
+
+__device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, size_t m_pitch, int w, int h, int x,
+                                             int* __restrict__ seam, int* __restrict__ seam_log,
+                                             float (*win)[32][DP_WIN], int lane)
+{
+    const float INF = __int_as_float(0x7f800000);
+    if (lane == 0) { seam[h - 1] = x; if (seam_log) seam_log[h - 1] = x; }
+    const int max_base = (int) m_pitch - DP_WIN;
+    // window rows of the batch that starts below image row ytop: window row i = image row ytop-1-i
+    auto stage = [&](int ytop, int xs, int buf) -> int {
+        int base = (xs - 66) & ~3;
+        base = base < 0 ? 0 : (base > max_base ? max_base : base);
+        if (ytop >= 1) {
+            for (int idx = lane; idx < 32 * (DP_WIN / 4); idx += 32) {
+                const int i = idx / (DP_WIN / 4), c = idx - i * (DP_WIN / 4);
+                const int yy = ytop - 1 - i;
+                if (yy >= 0) {
+                    const float* src = mplane + (size_t) yy * m_pitch + base + 4 * c;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(&win[buf][i][4 * c])), "l"(src) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        return base;
+    };
+    int buf = 0;
+    int base = stage(h - 1, x, 0);
+    for (int ytop = h - 1; ytop >= 1; ytop -= 32) {
+        const int base_next = stage(ytop - 32, x, buf ^ 1);     // lands while this batch is walked
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const int steps = ytop < 32 ? ytop : 32;
+        // the walk: three shared-memory reads and two compares per row; lane i remembers the column of step i and the
+        // 32 columns are written with one coalesced store at the end of the batch
+        int mine = 0;
+        for (int i = 0; i < steps; i++) {
+            const float* wr = win[buf][i] - base;
+            const float a = x > 0 ? wr[x - 1] : INF;
+            const float b = wr[x];
+            const float c = x < w - 1 ? wr[x + 1] : INF;
+            int arg = x - 1;
+            float best = a;
+            if (b < best) { best = b; arg = x; }
+            if (c < best) arg = x + 1;
+            x = arg;
+            if (lane == i) mine = x;
+        }
+        if (lane < steps) { seam[ytop - 1 - lane] = mine; if (seam_log) seam_log[ytop - 1 - lane] = mine; }
+        __syncwarp();
+        base = base_next;
+        buf ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 // TMA = true: the energies of a strip are staged DP_NST blocks of DP_R rows ahead into shared memory with 1-D bulk
 // async copies (cp.async.bulk, completion on an mbarrier per warp and stage) instead of a register ring of plain
@@ -181,7 +242,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     __shared__ __align__(8) unsigned long long ebar[DP_MAXW][DP_NST];
     __shared__ float red_v[DP_CL * DP_MAXW];      // per-strip minima, gathered in CTA 0 through distributed shared memory
     __shared__ int red_i[DP_CL * DP_MAXW];
-    __shared__ __align__(16) float win[32][DP_WIN];
+    __shared__ __align__(16) float win[2][32][DP_WIN];
     const int tid = threadIdx.x, lane = tid & 31;
     const int wpc = blockDim.x >> 5;                        // warps (strips) per CTA
     const uint32_t rank = dp_cta_rank();
@@ -382,44 +443,8 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
         }
-        // back-track (warp 0; every lane follows the same path, lane 0 records it)
-        int x = bi;
-        if (lane == 0) { seam[h - 1] = x; if (seam_log) seam_log[h - 1] = x; }
-        const int max_base = (int) m_pitch - DP_WIN;
-        for (int ytop = h - 1; ytop >= 1; ytop -= 32) {
-            // the parents of rows ytop, ytop-1, ... are chosen in rows ytop-1, ytop-2, ...: window row i = image row ytop-1-i
-            int base = (x - 36) & ~3;
-            base = base < 0 ? 0 : (base > max_base ? max_base : base);
-#pragma unroll
-            for (int hh = 0; hh < 2; hh++) {     // two chunks of 16 rows: 16 independent coalesced loads in flight per lane
-                float4 t[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int yy = ytop - 1 - (16 * hh + i);
-                    t[i] = (yy >= 0 && lane < DP_WIN / 4) ? __ldcg(reinterpret_cast<const float4*>(mplane + (size_t) yy * m_pitch + base) + lane)
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (lane < DP_WIN / 4) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) reinterpret_cast<float4*>(win[16 * hh + i])[lane] = t[i];
-                }
-            }
-            __syncwarp();
-            const int steps = ytop < 32 ? ytop : 32;
-            for (int i = 0; i < steps; i++) {
-                const float* wr = win[i] - base;
-                const float a = x > 0 ? wr[x - 1] : INF;
-                const float b = wr[x];
-                const float c = x < w - 1 ? wr[x + 1] : INF;
-                int arg = x - 1;
-                float best = a;
-                if (b < best) { best = b; arg = x; }
-                if (c < best) arg = x + 1;
-                x = arg;
-                if (lane == 0) { seam[ytop - 1 - i] = x; if (seam_log) seam_log[ytop - 1 - i] = x; }
-            }
-            __syncwarp();
-        }
+        // back-track (warp 0 of CTA 0)
+        dp_backtrack(mplane, m_pitch, w, h, bi, seam, seam_log, win, lane);
 #ifdef DCTC_SYNC_DEBUG
         if (tid == 0) {
             unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -503,7 +528,7 @@ __global__ void __launch_bounds__(32) dctc_seam_incr_kernel(const float* __restr
     int* xsb = reinterpret_cast<int*>(buf + 2 * (INCR_CAP + 4));           // first staged column per slot
     int* bmin = xsb + INCR_D;                                              // band of the removed seam per row
     int* bmax = bmin + h;
-    __shared__ __align__(16) float win[32][DP_WIN];
+    __shared__ __align__(16) float win[2][32][DP_WIN];
     const int lane = threadIdx.x;
     const float INF = __int_as_float(0x7f800000);
     if (lane == 0) *rebuild_flag = 0;
@@ -640,43 +665,7 @@ __global__ void __launch_bounds__(32) dctc_seam_incr_kernel(const float* __restr
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
     }
-    // back-track: same walk as in dctc_seam_dp_kernel (every lane follows the same path, lane 0 records it)
-    int x = bi;
-    if (lane == 0) { seam[h - 1] = x; if (seam_log) seam_log[h - 1] = x; }
-    const int max_base = (int) m_pitch - DP_WIN;
-    for (int ytop = h - 1; ytop >= 1; ytop -= 32) {
-        int base = (x - 36) & ~3;
-        base = base < 0 ? 0 : (base > max_base ? max_base : base);
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-            float4 t[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int yy = ytop - 1 - (16 * hh + i);
-                t[i] = (yy >= 0 && lane < DP_WIN / 4) ? __ldcg(reinterpret_cast<const float4*>(mplane + (size_t) yy * m_pitch + base) + lane)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (lane < DP_WIN / 4) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) reinterpret_cast<float4*>(win[16 * hh + i])[lane] = t[i];
-            }
-        }
-        __syncwarp();
-        const int steps = ytop < 32 ? ytop : 32;
-        for (int i = 0; i < steps; i++) {
-            const float* wr = win[i] - base;
-            const float a = x > 0 ? wr[x - 1] : INF;
-            const float b = wr[x];
-            const float c = x < w - 1 ? wr[x + 1] : INF;
-            int arg = x - 1;
-            float best = a;
-            if (b < best) { best = b; arg = x; }
-            if (c < best) arg = x + 1;
-            x = arg;
-            if (lane == 0) { seam[ytop - 1 - i] = x; if (seam_log) seam_log[ytop - 1 - i] = x; }
-        }
-        __syncwarp();
-    }
+    dp_backtrack(mplane, m_pitch, w, h, bi, seam, seam_log, win, lane);
 }
 
 // ---- visibility map + seam display ---------------------------------------------------
@@ -883,7 +872,7 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         ctx->launches++;
         ctx->c_vs_depth = 0;
     }
-    // cumulative-map plane, rows padded so that the 80-float back-track windows stay inside
+    // cumulative-map plane, rows padded so that the back-track windows (DP_WIN floats) stay inside
     const size_t m_pitch = ctx->c_en_pitch < (size_t) DP_WIN ? (size_t) DP_WIN : ctx->c_en_pitch;
     if (!ctx->c_m) {
         CK(ctx, cudaMalloc((void**) &ctx->c_m, sizeof(float) * m_pitch * (size_t) h));
@@ -909,7 +898,8 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     auto dp = P == 1 ? (tma ? dctc_seam_dp_kernel<1, true> : dctc_seam_dp_kernel<1, false>)
             : P == 2 ? (tma ? dctc_seam_dp_kernel<2, true> : dctc_seam_dp_kernel<2, false>)
                      : (tma ? dctc_seam_dp_kernel<4, true> : dctc_seam_dp_kernel<4, false>);
-    if (dp_smem > 40 * 1024) CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dp_smem));
+    // always opt in: the kernel's static shared memory (back-track windows) plus the dynamic part can exceed 48 KB
+    CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (dp_smem > 1024 ? dp_smem : 1024)));
     // incremental update (update_mmap): one warp; needs the band table of h rows twice in shared memory
     const size_t incr_smem = sizeof(float) * (INCR_D * 2 * INCR_SW + 2 * (INCR_CAP + 4)) + sizeof(int) * (INCR_D + 2 * (size_t) h);
     const bool incr_ok = ctx->c_incremental && incr_smem <= 160 * 1024;
