@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(NT) dctc_carve_rows_kernel(uint8_t* __restrict
 // (4*P adjacent cells per lane) and exchanges neighbours with warp shuffles only.  What the strip's edge lanes
 // cannot see contaminates one more column per row, so after DP_R rows the outer DP_R columns on each side are
 // garbage and the warp publishes only its central 128*P - 2*DP_R columns; every DP_R rows the warps exchange the
-// last row through shared memory (one barrier per DP_R rows) and restart with fresh halos.  Energies are
-// prefetched 8 rows ahead into registers; the cumulative rows go to a global float plane from which warp 0 re-derives
+// last row through shared memory (one barrier per DP_R rows) and restart with fresh halos.  Energies are staged
+// three blocks ahead by bulk async copies (TMA variant) or prefetched into a register ring; the cumulative rows go to a global float plane from which warp 0 re-derives
 // the parent choices during the back-track (dp_backtrack: 32-row batches through double-buffered shared-memory windows).
 // Cells outside the image hold +inf, which reproduces the range clipping.
 #ifndef DP_EXP
@@ -471,7 +471,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
 // MEASURED (1920x1080 noise, 480 seams): the walk recomputes ~150 columns per row on average and needs the full rebuild
 // for 2 of 480 seams, but ONE warp spends ~900 clk per row on it (phases per row: 250-470 clk row arithmetic, ~180 clk
 // side cells + next range, ~340 clk staging; a lone warp has no other warp to hide its 4-6 clk dependent-issue
-// latencies behind), i.e. 918 us per seam against 430 us for the cluster-wide rebuild.  It is therefore OFF by default
+// latencies behind), i.e. 918 us per seam against 283 us for the cluster-wide rebuild.  It is therefore OFF by default
 // (dctc_carver_set_incremental) and kept as the bit-identical reference point for a multi-warp block version.
 #ifndef DCTC_INCR_ABL
 #define DCTC_INCR_ABL 0   // timing ablations only
