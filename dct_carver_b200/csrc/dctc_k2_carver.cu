@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NT) dctc_carve_rows_kernel(uint8_t* __restrict
 #ifndef DP_EXP
 #define DP_EXP 0   // timing experiments only
 #endif
-constexpr int DP_R = 16;          // rows between two exchanges = halo columns on each side of a strip
+constexpr int DP_R = 32;          // rows between two exchanges = halo columns on each side of a strip
 constexpr int DP_MAXW = 8;        // warps per CTA of the DP cluster (256 threads: room for a deep register prefetch ring)
 
 constexpr int DP_CL = 8;          // CTAs of the cluster the strips are spread over (a lone SM can only pull ~35 GB/s from L2:
@@ -201,7 +201,7 @@ __device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, s
 // TMA = true: the energies of a strip are staged DP_NST blocks of DP_R rows ahead into shared memory with 1-D bulk
 // async copies (cp.async.bulk, completion on an mbarrier per warp and stage) instead of a register ring of plain
 // loads: nothing the cluster barrier's memory fence has to wait for, and 48 rows in flight per warp.
-constexpr int DP_NST = 3;
+constexpr int DP_NST = 2;
 
 __device__ __forceinline__ uint32_t dp_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 // bounded parity wait: a protocol error traps after ~2^24 polls instead of hanging the GPU
@@ -471,7 +471,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
 // MEASURED (1920x1080 noise, 480 seams): the walk recomputes ~150 columns per row on average and needs the full rebuild
 // for 2 of 480 seams, but ONE warp spends ~900 clk per row on it (phases per row: 250-470 clk row arithmetic, ~180 clk
 // side cells + next range, ~340 clk staging; a lone warp has no other warp to hide its 4-6 clk dependent-issue
-// latencies behind), i.e. 918 us per seam against 283 us for the cluster-wide rebuild.  It is therefore OFF by default
+// latencies behind), i.e. 918 us per seam against 245 us for the cluster-wide rebuild.  It is therefore OFF by default
 // (dctc_carver_set_incremental) and kept as the bit-identical reference point for a multi-warp block version.
 #ifndef DCTC_INCR_ABL
 #define DCTC_INCR_ABL 0   // timing ablations only
