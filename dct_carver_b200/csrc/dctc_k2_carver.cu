@@ -178,17 +178,24 @@ __device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, s
         // the walk: three shared-memory reads and two compares per row; lane i remembers the column of step i and the
         // 32 columns are written with one coalesced store at the end of the batch
         int mine = 0;
-        for (int i = 0; i < steps; i++) {
-            const float* wr = win[buf][i] - base;
-            const float a = x > 0 ? wr[x - 1] : INF;
-            const float b = wr[x];
-            const float c = x < w - 1 ? wr[x + 1] : INF;
+        const float* wb = &win[buf][0][0] - base;          // window row i, column x: wb[i * DP_WIN + x]
+        auto walk = [&](int i) {
+            const float* wr = wb + i * DP_WIN + x;
+            const float a = x > 0 ? wr[-1] : INF;
+            const float b = wr[0];
+            const float c = x < w - 1 ? wr[1] : INF;
             int arg = x - 1;
             float best = a;
             if (b < best) { best = b; arg = x; }
             if (c < best) arg = x + 1;
             x = arg;
             if (lane == i) mine = x;
+        };
+        if (steps == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) walk(i);          // fully unrolled: row offsets become immediates
+        } else {
+            for (int i = 0; i < steps; i++) walk(i);
         }
         if (lane < steps) { seam[ytop - 1 - lane] = mine; if (seam_log) seam_log[ytop - 1 - lane] = mine; }
         __syncwarp();

@@ -22,7 +22,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w, h, ch, seed = 4096, 2051, 3, 77
     ok = True
-    for b in (8, 16, 4):
+    for b in (8, 16, 4, 2):
         ctx = dc.Context(local, blocksize=b)
         for mode in ("peer", "exchange"):
             r = multigpu.BandRunner(ctx, dist, rank, world, w, h, ch, seed, mode=mode)
