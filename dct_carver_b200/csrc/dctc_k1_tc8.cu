@@ -64,6 +64,7 @@ struct alignas(128) TcSmem {
     __half B[4][64 * 16];            // Tz as UMMA K-major no-swizzle operands: [0] Bh, [1] Bl, [2]/[3] the K-swapped copies
     float2 L[2][4][LWP];             // luma of two groups: [buffer][row pair][column], .x = even row
     uint8_t Raw[3][8 * RawGeom<3>::ROW];
+    float park[16][MW];              // non-uniform weights: per-row quantities of the class rule parked by the consumers
     uint64_t bar_a_free, bar_a_free_lo, bar_d_full[2];
     uint32_t tmem_base;
     int work;
@@ -406,15 +407,26 @@ struct TcFold<true> {   // edges == textures: only the maximum matters
         }
     }
     __device__ __forceinline__ float result(int i, float we, float wt) const { (void) we; return m[i] * wt; }
+    __device__ __forceinline__ void set_park(float*) {}
 };
 
 template <>
 struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
-    float a[8], mm[8], bv[8], z[8];
+    // With A = |T[0][1]|, M = max|T[0][2..]|, Bv = |T[1][0]|, Z = max of the rest, the winner is a texture atom iff
+    //   Z >= max(A, M, Bv)  or  (Bv < max(A, M) and M >= A).
+    // A and M are final after the k1 = 0 tile, Bv after the k1 = 1 tile: max(A, M), the bit (M >= A) and Bv are parked
+    // (shared memory / one flag register) so that the six remaining tiles fold with the register budget of the
+    // uniform case (64 accumulator registers + 8 maxima) -- keeping all four quantities of all eight rows in
+    // registers spilled 1.2 KB per thread and made this variant four times slower than the uniform one.
+    float z[8];
+    unsigned flags;          // bit i: M >= A in row i
+    float* park;             // park[(which * 8 + i) * MW]: which = 0 max(A, M), 1 Bv; this thread's column
+    __device__ __forceinline__ void set_park(float* p) { park = p; }
     __device__ __forceinline__ void init()
     {
 #pragma unroll
-        for (int i = 0; i < 8; i++) { a[i] = 0.0f; mm[i] = -1.0f; bv[i] = 0.0f; z[i] = 0.0f; }
+        for (int i = 0; i < 8; i++) z[i] = 0.0f;
+        flags = 0u;
     }
     template <int K1>
     __device__ __forceinline__ void add(const uint32_t (&v)[64])
@@ -422,11 +434,14 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             if (K1 == 0) {
-                a[i] = fabsf(__uint_as_float(v[i * 8 + 1]));
+                const float a = fabsf(__uint_as_float(v[i * 8 + 1]));
+                float mm = -1.0f;
 #pragma unroll
-                for (int k2 = 2; k2 < 8; k2++) mm[i] = fmaxf(mm[i], fabsf(__uint_as_float(v[i * 8 + k2])));
+                for (int k2 = 2; k2 < 8; k2++) mm = fmaxf(mm, fabsf(__uint_as_float(v[i * 8 + k2])));
+                park[i * MW] = fmaxf(a, mm);
+                if (mm >= a) flags |= 1u << i;
             } else {
-                if (K1 == 1) bv[i] = fabsf(__uint_as_float(v[i * 8]));
+                if (K1 == 1) park[(8 + i) * MW] = fabsf(__uint_as_float(v[i * 8]));
                 else z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[i * 8])));
 #pragma unroll
                 for (int k2 = 1; k2 < 8; k2++) z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[i * 8 + k2])));
@@ -435,9 +450,9 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
     }
     __device__ __forceinline__ float result(int i, float we, float wt) const
     {
-        const float am = fmaxf(a[i], mm[i]);
-        const float top = fmaxf(fmaxf(am, bv[i]), z[i]);
-        const bool tex = (z[i] >= fmaxf(am, bv[i])) || (!(bv[i] >= am) && (mm[i] >= a[i]));
+        const float am = park[i * MW], bv = park[(8 + i) * MW];
+        const float top = fmaxf(fmaxf(am, bv), z[i]);
+        const bool tex = (z[i] >= fmaxf(am, bv)) || (!(bv >= am) && ((flags >> i) & 1u));
         return top * (tex ? wt : we);
     }
 };
@@ -564,6 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         for (int st = 0; st < nsteps; st++) {
             TcFold<UNIFORM> f;
             f.init();
+            f.set_park(&s.park[0][px]);
             bar_step_sync();                                  // the MMA warp has started this step
             consume_k1<0, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
             consume_k1<1, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
