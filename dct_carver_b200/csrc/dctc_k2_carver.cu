@@ -900,7 +900,8 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     const int wpc = (strips + DP_CL - 1) / DP_CL;
     // energies staged by bulk async copies when the DP_NST stages of every warp fit into shared memory
     const size_t tma_smem = sizeof(float) * ((size_t) wpc * DP_NST * DP_R * 128 * P);
-    const bool tma = sizeof(float) * 2 * (size_t) wpc * wout + tma_smem <= 200 * 1024 && !getenv("DCTC_DP_NO_TMA");
+    // (the kernel also has ~38 KB of static shared memory: back-track windows, reduction scratch, mbarriers)
+    const bool tma = sizeof(float) * 2 * (size_t) wpc * wout + tma_smem <= 180 * 1024 && !getenv("DCTC_DP_NO_TMA");
     const size_t dp_smem = sizeof(float) * 2 * (size_t) wpc * wout + (tma ? tma_smem : 0);
     auto dp = P == 1 ? (tma ? dctc_seam_dp_kernel<1, true> : dctc_seam_dp_kernel<1, false>)
             : P == 2 ? (tma ? dctc_seam_dp_kernel<2, true> : dctc_seam_dp_kernel<2, false>)

@@ -13,7 +13,7 @@ w, h, ch = 3840, 2160, 3
 d_in = ctx.dev_alloc(F * w * h * ch)
 d_out = ctx.dev_alloc(F * w * h * 4)
 ctx.synth_fill_dev(d_in, F, w * h * ch, w, h, ch, w * ch, 77, 0)
-ctx.set_params(b, 0.5, 0.5)
+ctx.set_params(b, float(os.environ.get('DCTC_EDGES', 0.5)), float(os.environ.get('DCTC_TEXTURES', 0.5)))
 for _ in range(2):
     ctx.energy_batch_dev(d_in, F, w * h * ch, w, h, ch, w * ch, d_out, w * h, w)
 ctx.sync()
