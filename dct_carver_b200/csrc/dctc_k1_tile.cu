@@ -131,6 +131,18 @@ cudaError_t dctc_launch_k1_tile(const DctcK1Args& a, int blocksize, int n_frames
 {
     if (a.w <= 0 || a.h <= 0 || n_frames <= 0) return cudaSuccess;
     if (n_frames > 65535 || (a.h + 31) / 32 > 65535) return cudaErrorInvalidConfiguration;
+    if (a.seam) {
+        // band mode (per-seam update): ~10 x 1080 pixels in all, so the launch is pure latency -- small tiles with two
+        // pixels per thread keep the per-thread chain short (8 k1 x 2 instead of 8 k1 x 8 transforms for b = 8); the
+        // arithmetic per pixel is the same as in the full-map configuration (bit-identical energies)
+        switch (blocksize) {
+        case 2: return launch_tile<2, 32, 16, 2>(a, n_frames, uniform, stream);
+        case 4: return launch_tile<4, 32, 16, 2>(a, n_frames, uniform, stream);
+        case 8: return launch_tile<8, 32, 16, 2>(a, n_frames, uniform, stream);
+        case 16: return launch_tile<16, 32, 16, 2>(a, n_frames, uniform, stream);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (blocksize) {
     case 2: return launch_tile<2, 64, 32, 8>(a, n_frames, uniform, stream);
     case 4: return launch_tile<4, 64, 32, 8>(a, n_frames, uniform, stream);
