@@ -205,10 +205,10 @@ __device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, s
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// TMA = true: the energies of a strip are staged DP_NST blocks of DP_R rows ahead into shared memory with 1-D bulk
+// TMA = true: the energies of a strip are staged nst chunks of DP_SR rows ahead into shared memory with 1-D bulk
 // async copies (cp.async.bulk, completion on an mbarrier per warp and stage) instead of a register ring of plain
 // loads: nothing the cluster barrier's memory fence has to wait for, and 48 rows in flight per warp.
-constexpr int DP_NST = 2;
+constexpr int DP_NST_MAX = 4;     // stages per warp: as many (2..4) as fit into shared memory, chosen by the host
 
 __device__ __forceinline__ uint32_t dp_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 // bounded parity wait: a protocol error traps after ~2^24 polls instead of hanging the GPU
@@ -230,23 +230,27 @@ __device__ __forceinline__ void dp_mbar_wait(uint32_t bar, uint32_t parity)
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
-template <int DP_P, bool TMA>     // DP_P float4 groups per lane: strip = 128 * DP_P columns, 128 * DP_P - 32 of them published
+// DP_P float4 groups per lane: strip = 128 * DP_P columns, 128 * DP_P - 2 * DP_R of them published.
+// DP_SR: rows per staged chunk of the bulk-copy variant (32 when two stages per warp fit, else 16), 0 = register ring.
+template <int DP_P, int DP_SR>
 __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dctc_seam_dp_kernel(const float* __restrict__ en, size_t en_pitch, int w, int h,
                                                                     float* __restrict__ mplane, size_t m_pitch,
                                                                     int* __restrict__ seam, int* __restrict__ seam_log,
-                                                                    int* __restrict__ run_flag)
+                                                                    int* __restrict__ run_flag, int nst)
 {
     // fallback of the incremental update (dctc_seam_incr_kernel): runs only when that kernel asked for a rebuild
     if (run_flag && *run_flag == 0) return;       // uniform over the cluster, before any cluster barrier
     if (run_flag && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(run_flag + 1, 1);   // rebuilds since the session was loaded
+    constexpr bool TMA = DP_SR > 0;
+    constexpr int SRD = TMA ? DP_SR : DP_R;       // (divisor that is never zero)
     constexpr int CPL = 4 * DP_P;                 // cells per lane
     constexpr int STRIP = 32 * CPL;               // columns a warp computes
     constexpr int WOUT = STRIP - 2 * DP_R;        // columns a warp publishes
     constexpr int HL = DP_R / CPL;                // halo lanes on each side (DP_R is a multiple of CPL)
     constexpr int PF = TMA ? 1 : 16 / DP_P;       // energy rows in flight per lane (register ring of the non-TMA variant)
     extern __shared__ __align__(128) float xrow[]; // two exchange rows of (warps per CTA * WOUT) floats, double buffered;
-                                                  // TMA: followed by warps x DP_NST stages x DP_R rows x STRIP energies
-    __shared__ __align__(8) unsigned long long ebar[DP_MAXW][DP_NST];
+                                                  // TMA: followed by warps x nst stages x DP_SR rows x STRIP energies
+    __shared__ __align__(8) unsigned long long ebar[DP_MAXW][DP_NST_MAX];
     __shared__ float red_v[DP_CL * DP_MAXW];      // per-strip minima, gathered in CTA 0 through distributed shared memory
     __shared__ int red_i[DP_CL * DP_MAXW];
     __shared__ __align__(16) float win[2][32][DP_WIN];
@@ -290,20 +294,19 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     const int cs = warp * WOUT - DP_R;
     const int tx0 = max(cs, 0), tx1 = min(cs + STRIP, (int) en_pitch);
     const int tbytes = tx1 > tx0 ? (tx1 - tx0) * 4 : 0;
-    float* estage = xrow + 2 * xlen + (size_t) (tid >> 5) * DP_NST * DP_R * STRIP;
-    const int nblocks = (h - 1 + DP_R - 1) / DP_R;
-    auto issue_block = [&](int blk) {       // rows 1 + blk * DP_R .. (clamped to h - 1) -> stage blk % DP_NST
-        const int st = blk % DP_NST;
+    float* estage = xrow + 2 * xlen + (size_t) (tid >> 5) * nst * SRD * STRIP;
+    const int nchunks = (h - 1 + SRD - 1) / SRD;
+    auto issue_chunk = [&](int ch, int st) {   // rows 1 + ch * DP_SR .. (clamped to h - 1) -> stage st = ch % nst
         const uint32_t bar = dp_smem_u32(&ebar[tid >> 5][st]);
         if (lane == 0) {
-            if (tbytes > 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (tbytes * DP_R)) : "memory");
+            if (tbytes > 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (tbytes * SRD)) : "memory");
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
         }
         __syncwarp();
-        if (lane < DP_R && tbytes > 0) {
-            const int y = min(1 + blk * DP_R + lane, hm1);
+        if (lane < SRD && tbytes > 0) {
+            const int y = min(1 + ch * SRD + lane, hm1);
             const float* src = en + (size_t) y * en_pitch + tx0;
-            const uint32_t dst = dp_smem_u32(estage + ((size_t) st * DP_R + lane) * STRIP + (tx0 - cs));
+            const uint32_t dst = dp_smem_u32(estage + ((size_t) st * SRD + lane) * STRIP + (tx0 - cs));
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(src), "r"((uint32_t) tbytes), "r"(bar) : "memory");
         }
@@ -311,11 +314,11 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     if (TMA) {
         if (lane == 0) {
 #pragma unroll
-            for (int st = 0; st < DP_NST; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&ebar[tid >> 5][st])) : "memory");
+            for (int st = 0; st < DP_NST_MAX; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&ebar[tid >> 5][st])) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        for (int blk = 0; blk < DP_NST && blk < nblocks; blk++) issue_block(blk);
+        for (int ch = 0; ch < nst && ch < nchunks; ch++) issue_chunk(ch, ch);
     }
 
     float4 cur[DP_P], e[PF][DP_P];
@@ -336,18 +339,22 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
 #endif
     float* mrow = mplane + m_pitch;
     int xb = 0;
-    int blk = 0;
-    for (int yb = 1; yb < h; yb += DP_R, blk++) {
-        const float* stg = estage + (size_t) (blk % DP_NST) * DP_R * STRIP + lane * CPL;
-        if (TMA) dp_mbar_wait(dp_smem_u32(&ebar[tid >> 5][blk % DP_NST]), (uint32_t) ((blk / DP_NST) & 1));
+    int c_ch = 0, c_st = 0;                          // chunk being consumed, its stage and mbarrier parity
+    uint32_t c_par = 0;
+    for (int yb = 1; yb < h; yb += DP_R) {
+        const float* stg = estage;
 #pragma unroll
         for (int kk = 0; kk < DP_R; kk++) {
             const int k = kk % PF;
             const int y = yb + kk;
+            if (TMA && kk % SRD == 0 && y < h) {                          // a new chunk of staged rows starts here
+                dp_mbar_wait(dp_smem_u32(&ebar[tid >> 5][c_st]), c_par);
+                stg = estage + (size_t) c_st * SRD * STRIP + lane * CPL;
+            }
             if (y < h) {                                                    // uniform across the CTA
                 if (TMA) {
 #pragma unroll
-                    for (int g = 0; g < DP_P; g++) e[0][g] = *reinterpret_cast<const float4*>(stg + kk * STRIP + 4 * g);
+                    for (int g = 0; g < DP_P; g++) e[0][g] = *reinterpret_cast<const float4*>(stg + (kk % SRD) * STRIP + 4 * g);
                 }
                 // neighbours across lanes; the strip's outermost lanes see +inf (their cells are never published)
                 float l = __shfl_up_sync(0xffffffffu, cur[DP_P - 1].w, 1);
@@ -384,12 +391,14 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
                 }
                 mrow += m_pitch;
             }
-        }
-        if (TMA) {                                   // this warp is done with the stage: refill it DP_NST blocks ahead
-            __syncwarp();
-            if (blk + DP_NST < nblocks) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue_block(blk + DP_NST);
+            if (TMA && kk % SRD == SRD - 1) {    // this warp is done with the chunk: refill its stage nst chunks ahead
+                __syncwarp();
+                if (c_ch + nst < nchunks) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue_chunk(c_ch + nst, c_st);
+                }
+                c_ch++;
+                if (++c_st == nst) { c_st = 0; c_par ^= 1u; }
             }
         }
         // exchange the last row of the block: every warp publishes its central cells, then reloads its whole strip
@@ -898,14 +907,26 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     const int wout = 128 * P - 2 * DP_R;
     const int strips = (wcur + wout - 1) / wout;
     const int wpc = (strips + DP_CL - 1) / DP_CL;
-    // energies staged by bulk async copies when the DP_NST stages of every warp fit into shared memory
-    const size_t tma_smem = sizeof(float) * ((size_t) wpc * DP_NST * DP_R * 128 * P);
+    // energies staged by bulk async copies when at least two stages (DP_SR rows each) per warp fit into shared memory
     // (the kernel also has ~38 KB of static shared memory: back-track windows, reduction scratch, mbarriers)
-    const bool tma = sizeof(float) * 2 * (size_t) wpc * wout + tma_smem <= 180 * 1024 && !getenv("DCTC_DP_NO_TMA");
-    const size_t dp_smem = sizeof(float) * 2 * (size_t) wpc * wout + (tma ? tma_smem : 0);
-    auto dp = P == 1 ? (tma ? dctc_seam_dp_kernel<1, true> : dctc_seam_dp_kernel<1, false>)
-            : P == 2 ? (tma ? dctc_seam_dp_kernel<2, true> : dctc_seam_dp_kernel<2, false>)
-                     : (tma ? dctc_seam_dp_kernel<4, true> : dctc_seam_dp_kernel<4, false>);
+    const size_t xrow_smem = sizeof(float) * 2 * (size_t) wpc * wout;
+    int nst = 0, sr = 0;
+    if (!getenv("DCTC_DP_NO_TMA")) {
+        const size_t row_smem = sizeof(float) * ((size_t) wpc * 128 * P);      // one staged row of every warp
+        const size_t budget = 180 * 1024 - xrow_smem;
+        if (2 * 32 * row_smem <= budget) { sr = 32; nst = 2; }                 // whole 32-row blocks, two in flight
+        else {
+            sr = 16;
+            for (nst = DP_NST_MAX; nst >= 2 && (size_t) nst * 16 * row_smem > budget; nst--) {}
+            if (nst < 2) { sr = 0; nst = 0; }
+        }
+    }
+    const size_t dp_smem = xrow_smem + sizeof(float) * ((size_t) nst * sr * wpc * 128 * P);
+    using dp_fn = void (*)(const float*, size_t, int, int, float*, size_t, int*, int*, int*, int);
+    static const dp_fn table[3][3] = {{dctc_seam_dp_kernel<1, 0>, dctc_seam_dp_kernel<1, 16>, dctc_seam_dp_kernel<1, 32>},
+                                      {dctc_seam_dp_kernel<2, 0>, dctc_seam_dp_kernel<2, 16>, dctc_seam_dp_kernel<2, 32>},
+                                      {dctc_seam_dp_kernel<4, 0>, dctc_seam_dp_kernel<4, 16>, dctc_seam_dp_kernel<4, 32>}};
+    const dp_fn dp = table[P == 1 ? 0 : P == 2 ? 1 : 2][sr / 16];
     // always opt in: the kernel's static shared memory (back-track windows) plus the dynamic part can exceed 48 KB
     CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (dp_smem > 1024 ? dp_smem : 1024)));
     // incremental update (update_mmap): one warp; needs the band table of h rows twice in shared memory
@@ -924,11 +945,11 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
             // update_mmap + build_vpath: walk the changed cells only; the full rebuild below runs only if the walk gave up
             dctc_seam_incr_kernel<<<1, 32, incr_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, r,
                                                                      ctx->c_seam, log_s, ctx->c_band);
-            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, ctx->c_band);
+            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, ctx->c_band, nst);
             ctx->launches++;
         } else {
             // build_mmap + build_vpath
-            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr);
+            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr, nst);
         }
 #ifdef DCTC_SYNC_DEBUG
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }

@@ -145,7 +145,7 @@ def test_gpu_retarget_height_and_energy_image(ctx):
 
 @pytest.mark.parametrize("b,ch,w,h,n", [(8, 3, 150, 90, 25), (8, 1, 97, 75, 40), (4, 3, 64, 33, 10), (16, 3, 130, 70, 12),
                                         (8, 3, 1100, 40, 30), (8, 3, 40, 300, 8), (2, 1, 9, 1, 3),
-                                        (8, 1, 4200, 20, 3), (8, 1, 5000, 40, 2), (4, 1, 13000, 12, 2)])
+                                        (8, 1, 4200, 20, 3), (8, 1, 5000, 40, 2), (4, 1, 13000, 12, 2), (8, 3, 3840, 70, 3), (8, 1, 2600, 50, 3)])
 def test_device_seam_loop_equals_host_carver(ctx, b, ch, w, h, n):
     """dctc_carver_resize_width (seam DP + back-track + carve + band update, all on the device) must remove exactly
     the seams the host carver (liblqr stand-in, incremental cumulative map on the CPU) removes: same tie rules

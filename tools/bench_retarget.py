@@ -10,6 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import dct_carver_b200 as dc  # noqa: E402
+if os.environ.get("DCTC_LIB"):
+    dc.LIB_PATH = os.environ["DCTC_LIB"]
 from dct_carver_b200 import host  # noqa: E402
 import oracle_lib as ol  # noqa: E402  (synthetic image generator only)
 
