@@ -77,16 +77,38 @@ __global__ void __launch_bounds__(TW* TH / P) dctc_k1_tile_kernel(const DctcK1Ar
     DctcTracker<UNIFORM> tr[P];
 #pragma unroll
     for (int p = 0; p < P; p++) tr[p].init();
+    if (B >= 8) {
+        // two k1 planes per packed FP32x2 transform (same operations and rounding as the scalar transform, half the
+        // instructions): X2[k2] = (T[k1][k2], T[k1+1][k2])
 #pragma unroll
-    for (int k1 = 0; k1 < B; k1++) {
-        float col[P + B - 1];
+        for (int k1 = 0; k1 < B; k1 += 2) {
+            float2 col2[P + B - 1];
 #pragma unroll
-        for (int j = 0; j < P + B - 1; j++) col[j] = Hs[(k1 * LH + y0 + j) * TW + x];
+            for (int j = 0; j < P + B - 1; j++)
+                col2[j] = make_float2(Hs[(k1 * LH + y0 + j) * TW + x], Hs[((k1 + 1) * LH + y0 + j) * TW + x]);
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            float X[B];
-            dctc_dct_fwd<B>(col + p, X);
-            if (a.preview) tr[p].template add_t<B>(k1, X); else tr[p].template add<B>(k1, X);
+            for (int p = 0; p < P; p++) {
+                float2 X2[B];
+                dctc_dct_fwd2<(B >= 8 ? B : 8)>(col2 + p, X2);
+                float Xa[B], Xb[B];
+#pragma unroll
+                for (int k = 0; k < B; k++) { Xa[k] = X2[k].x; Xb[k] = X2[k].y; }
+                if (a.preview) { tr[p].template add_t<B>(k1, Xa); tr[p].template add_t<B>(k1 + 1, Xb); }
+                else { tr[p].template add<B>(k1, Xa); tr[p].template add<B>(k1 + 1, Xb); }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k1 = 0; k1 < B; k1++) {
+            float col[P + B - 1];
+#pragma unroll
+            for (int j = 0; j < P + B - 1; j++) col[j] = Hs[(k1 * LH + y0 + j) * TW + x];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                float X[B];
+                dctc_dct_fwd<B>(col + p, X);
+                if (a.preview) tr[p].template add_t<B>(k1, X); else tr[p].template add<B>(k1, X);
+            }
         }
     }
     const int gx = tx0 + x;
