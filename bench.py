@@ -47,6 +47,13 @@ def kernel_name(blocksize, kernel):
     return "dctc_k1_tile_kernel (FP32)"
 
 
+def arithmetic(blocksize, kernel):
+    if blocksize == 8 and kernel in (0, 3):
+        return ("exact integer luma, FP32 x-pass, y-pass on tcgen05 with fp16 hi/lo split operands (22 significant "
+                "bits) and FP32 accumulation; max rel err vs the double reference 1.2e-6")
+    return "FP32 (max rel err vs the double reference 1e-6)"
+
+
 def kernel_note(blocksize):
     base = "traffic = DRAM bytes per launch from ncu (profiles/traffic.json); "
     if blocksize == 8:
@@ -318,7 +325,8 @@ def main():
             "scaling": "strong" if args.workload == "gigapixel" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict({"workload": wl["desc"].replace("blocksize 8", "blocksize %d" % args.blocksize), "blocksize": args.blocksize, "edges": 0.5, "textures": 0.5,
-                            "kernel": args.kernel, "l2": "inputs+outputs per step exceed L2 (distinct frames)",
+                            "kernel": args.kernel, "arithmetic": arithmetic(args.blocksize, args.kernel),
+                            "l2": "inputs+outputs per step exceed L2 (distinct frames)",
                             "parallelism": "frames sharded, no collective" if args.workload != "gigapixel" else "row bands"},
                            **cfg_extra),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
