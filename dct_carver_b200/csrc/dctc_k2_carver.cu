@@ -5,6 +5,7 @@
 // within +-radius of the seam (radius = blocksize/2, registered at src/render.c:314-315).  Here the image and the
 // energy plane stay resident in HBM; one kernel compacts both over the seam, then the K1 tile kernel runs in band
 // mode over just the touched pixels, with arithmetic identical to a full recompute (bit-identical results).
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -236,7 +237,8 @@ template <int DP_P, int DP_SR>
 __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dctc_seam_dp_kernel(const float* __restrict__ en, size_t en_pitch, int w, int h,
                                                                     float* __restrict__ mplane, size_t m_pitch,
                                                                     int* __restrict__ seam, int* __restrict__ seam_log,
-                                                                    int* __restrict__ run_flag, int nst)
+                                                                    int* __restrict__ run_flag, int nst,
+                                                                    const __grid_constant__ CUtensorMap tmap, int use_tmap)
 {
     // fallback of the incremental update (dctc_seam_incr_kernel): runs only when that kernel asked for a rebuild
     if (run_flag && *run_flag == 0) return;       // uniform over the cluster, before any cluster barrier
@@ -298,6 +300,17 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     const int nchunks = (h - 1 + SRD - 1) / SRD;
     auto issue_chunk = [&](int ch, int st) {   // rows 1 + ch * DP_SR .. (clamped to h - 1) -> stage st = ch % nst
         const uint32_t bar = dp_smem_u32(&ebar[tid >> 5][st]);
+        if (use_tmap) {
+            // one 2-D tensor copy (box = STRIP columns x DP_SR rows; columns left of the image and rows below it are
+            // zero-filled by the TMA unit) instead of DP_SR row copies, which the hardware issues one elected lane at a time
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (SRD * STRIP * 4)) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(dp_smem_u32(estage + (size_t) st * SRD * STRIP)), "l"(&tmap), "r"(cs), "r"(1 + ch * SRD), "r"(bar) : "memory");
+            }
+            __syncwarp();
+            return;
+        }
         if (lane == 0) {
             if (tbytes > 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (tbytes * SRD)) : "memory");
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -922,11 +935,34 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         }
     }
     const size_t dp_smem = xrow_smem + sizeof(float) * ((size_t) nst * sr * wpc * 128 * P);
-    using dp_fn = void (*)(const float*, size_t, int, int, float*, size_t, int*, int*, int*, int);
+    using dp_fn = void (*)(const float*, size_t, int, int, float*, size_t, int*, int*, int*, int, const CUtensorMap, int);
     static const dp_fn table[3][3] = {{dctc_seam_dp_kernel<1, 0>, dctc_seam_dp_kernel<1, 16>, dctc_seam_dp_kernel<1, 32>},
                                       {dctc_seam_dp_kernel<2, 0>, dctc_seam_dp_kernel<2, 16>, dctc_seam_dp_kernel<2, 32>},
                                       {dctc_seam_dp_kernel<4, 0>, dctc_seam_dp_kernel<4, 16>, dctc_seam_dp_kernel<4, 32>}};
     const dp_fn dp = table[P == 1 ? 0 : P == 2 ? 1 : 2][sr / 16];
+    // tensor map of the energy plane for the staged variant (strips of up to 256 columns: the TMA box limit)
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int use_tmap = 0;
+    if (sr > 0 && 128 * P <= 256 && !getenv("DCTC_DP_NO_TENSORMAP")) {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) == cudaSuccess && fp &&
+            qres == cudaDriverEntryPointSuccess) {
+            const cuuint64_t gdim[2] = {(cuuint64_t) ctx->c_en_pitch, (cuuint64_t) h};
+            const cuuint64_t gstr[1] = {(cuuint64_t) ctx->c_en_pitch * sizeof(float)};
+            const cuuint32_t box[2] = {(cuuint32_t) (128 * P), (cuuint32_t) sr};
+            const cuuint32_t estr[2] = {1, 1};
+            if (((encode_fn) fp)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ctx->c_en, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                use_tmap = 1;
+        } else {
+            (void) cudaGetLastError();
+        }
+    }
     // always opt in: the kernel's static shared memory (back-track windows) plus the dynamic part can exceed 48 KB
     CK(ctx, cudaFuncSetAttribute(dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (dp_smem > 1024 ? dp_smem : 1024)));
     // incremental update (update_mmap): one warp; needs the band table of h rows twice in shared memory
@@ -945,11 +981,11 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
             // update_mmap + build_vpath: walk the changed cells only; the full rebuild below runs only if the walk gave up
             dctc_seam_incr_kernel<<<1, 32, incr_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, r,
                                                                      ctx->c_seam, log_s, ctx->c_band);
-            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, ctx->c_band, nst);
+            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, ctx->c_band, nst, tmap, use_tmap);
             ctx->launches++;
         } else {
             // build_mmap + build_vpath
-            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr, nst);
+            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr, nst, tmap, use_tmap);
         }
 #ifdef DCTC_SYNC_DEBUG
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }
