@@ -1,0 +1,724 @@
+// K1-TC wide (block size 8, full maps; ONE CTA per SM with all 512 TMEM columns -- experimental sibling of dctc_k1_tc8.cu):
+// 3-position operand ring (+ a duplicate of position 0 so that every step's 16 window rows are contiguous columns),
+// four accumulator tiles, 8 producer / 8 consumer warps.  Same operator and arithmetic as dctc_k1_tc8.cu.
+// K1-TC (block size 8, full maps): the y-pass of the block DCT on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Same operator as dctc_k1_march8.cu / dctc_k1_tile.cu (reference chain src/render.c:134-157 -> src/dct.c:77-110 ->
+// ddct8x8s, src/fft2d/shrtdct.c:61-117).  A CTA owns a strip of 128 columns and marches down its segment 8 rows
+// ("a group") at a time; pixel column x0+m is row m of every MMA (TMEM lane m).
+//
+//   converter warps 9-10: cp.async the raw rows two groups ahead (triple-buffered), convert one group to luma
+//       (four pixels x two rows per task: 32-bit shared loads, PRMT + FADD byte->float, no XU-pipe conversions) and
+//       hand the luma row pairs to the producers through hardware named barriers (double-buffered)
+//   producer warps 0-3 (thread = column): run the
+//       x-pass (one packed FP32x2 DCT-8 per row pair), split each coefficient H[k1] into fp16 hi + fp16 lo
+//       (hi = rn16(H), lo = rn16(H - hi): 22 significant bits) and store the group into the TMEM A operand ring
+//       with tcgen05.st: columns [k1][hi|lo][slot g&1][row pair], two consecutive rows per 32-bit column
+//   MMA warp 8 (one elected thread): for every k1, D[128 x 64] = A_k1[128 x 16] * Tz[16 x 64] with
+//       Tz[y'][(i,k2)] = B8[k2][y'-i] (Toeplitz expansion of the DCT basis: output row i of the group reads window
+//       rows i..i+7 of the 16 staged rows), as three kind::f16 MMAs with FP32 accumulation in TMEM:
+//       hi*Bh + lo*Bh + hi*Bl (the dropped lo*Bl term is 2^-22 relative).  Odd steps use the K-swapped copy of Tz
+//       because the older group then sits in ring slot 1.
+//   consumer warps 4-7 (thread = column): tcgen05.ld the 64 accumulators of (8 rows x 8 k2), fold |.|-max over k2
+//       and k1 with FMNMX3 (or the last-arg-max class tracker when edges != textures), scale, coalesced store.
+//
+// Per pixel the CUDA cores execute ~100 instructions instead of the ~264 of the FP32 march kernel; the tensor pipe
+// does 24 M128 N64 K16 MMAs per 1024 pixels (36.3 clk each measured, profiles/r01_tcgen05_probe2.txt).
+#include <cuda_fp16.h>
+#include <cstdio>
+#include "dctc_common.cuh"
+#include "dctc_launch.h"
+#include "dctc_tc_tables.cuh"
+
+namespace {
+
+// -DDCTC_TC_TIMING: per-role wait-cycle accounting (clock64), printed by CTA 0 when it retires (tools/time_tc.py)
+#ifdef DCTC_TC_TIMING
+#define TT_T0() const long long tt_b = clock64()
+#define TT_ACC(role, k) g_tt_acc[k] += clock64() - tt_b
+#define TT_DECL() long long g_tt_acc[4] = {0, 0, 0, 0}; const long long tt_start = clock64()
+#define TT_REPORT(role, cond)                                                                                          \
+    if (blockIdx.x == 0 && (cond))                                                                                     \
+        printf("role %d: total %lld clk, waits %lld %lld %lld %lld\n", role, clock64() - tt_start, g_tt_acc[0], g_tt_acc[1], g_tt_acc[2], g_tt_acc[3])
+#else
+#define TT_T0()
+#define TT_ACC(role, k)
+#define TT_DECL() long long* const g_tt_acc = nullptr
+#define TT_REPORT(role, cond)
+#endif
+
+constexpr int MW = 128;            // columns per CTA = MMA M
+constexpr int LWP = MW + 8;        // staged luma row: index i <-> column x0-4+i (index 0 is a pad, 1..135 are read)
+constexpr int NTHREADS = 896;      // 8 producer warps, 16 consumer warps, 1 MMA warp, 3 converter warps
+constexpr int WARP_MMA = 24;
+constexpr int NR = 4;              // output rows per consumer warp (half a tile)
+constexpr int NCONV = 96;          // converter threads
+constexpr int NQUAD = 34;          // 4-pixel groups per staged row: columns x0-4 .. x0+131
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TM_A = 0;       // A ring: (k1*2 + part)*16 + pos*4 + pair, pos 0..2 = group % 3, pos 3 = copy of pos 0
+constexpr uint32_t TM_D = 256;     // four accumulator tiles of 64 columns
+constexpr int PAD_SMEM = 120 * 1024;  // dynamic shared memory requested only to cap residency at 2 CTAs/SM (2 x 256 TMEM columns)
+
+template <int CH>
+struct RawGeom {
+    static constexpr int CHUNKS = (16 + (MW + 4) * CH + 15) / 16;   // 16-byte chunks per staged raw row
+    static constexpr int ROW = CHUNKS * 16;
+};
+
+struct alignas(128) TcSmem {
+    __half B[2][64 * 16];            // Tz as UMMA K-major no-swizzle operands: [0] Bh, [1] Bl, [2]/[3] the K-swapped copies
+    float2 L[2][4][LWP];             // luma of two groups: [buffer][row pair][column], .x = even row
+    uint8_t Raw[3][8 * RawGeom<3>::ROW];
+    float park[2][2][8][MW];         // partial folds of the odd-k1 consumer sets: [step parity][tile half][4 maxima + 4 Bv][column]              // non-uniform weights: per-row quantities of the class rule parked by the consumers
+    uint64_t bar_a_free[3], bar_d_full[4];
+    uint32_t tmem_base;
+    int work;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_inval(uint32_t bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// Tight parity wait (labels are local to the braces).  try_wait suspends the warp in hardware for a bounded time per
+// attempt; after 2^22 failed attempts (seconds) a protocol error traps, so the launch fails instead of hanging.
+#ifdef DCTC_TC_DEBUG
+__device__ __noinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0)
+{
+    for (uint32_t n = 0;; n++) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (n > (1u << 20)) { printf("mbar timeout tag %d parity %u block %d thread %d\n", tag, parity, blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+#else
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0)
+{
+    (void) tag;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "DCTC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DCTC_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DCTC_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DCTC_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DCTC_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 0x100000;\n"
+        "@p bra DCTC_WAIT;\n"
+        "trap;\n"
+        "DCTC_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+#endif
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Named barriers: 2,3 accumulator tiles; 4 converter threads; 5,6 luma buffer full; 7,8 luma buffer free; 9 step started
+// (MMA warp -> consumers: they block here instead of polling bar_d_full during the producers' phase); 10 operands of a
+// group stored (producers -> MMA warp).  A blocked bar.sync costs no issue slots, unlike an mbarrier poll loop.
+__device__ __forceinline__ void bar_step_arrive() { asm volatile("bar.arrive 9, 544;" ::: "memory"); }
+__device__ __forceinline__ void bar_step_sync() { asm volatile("bar.sync 9, 544;" ::: "memory"); }
+__device__ __forceinline__ void bar_afull_arrive() { asm volatile("bar.arrive 10, 288;" ::: "memory"); }
+__device__ __forceinline__ void bar_afull_sync() { asm volatile("bar.sync 10, 288;" ::: "memory"); }
+// 13,14: the two consumer sets that share the rows of one tile half combine their partial maxima
+__device__ __forceinline__ void bar_pair_arrive(int h) { asm volatile("bar.arrive %0, 256;" ::"r"(13 + h) : "memory"); }
+__device__ __forceinline__ void bar_pair_sync(int h) { asm volatile("bar.sync %0, 256;" ::"r"(13 + h) : "memory"); }
+__device__ __forceinline__ void bar_converters() { asm volatile("bar.sync 6, 96;" ::: "memory"); }
+__device__ __forceinline__ void bar_lfull_arrive(int b) { asm volatile("bar.arrive %0, 352;" ::"r"(7 + b) : "memory"); }
+__device__ __forceinline__ void bar_lfull_sync(int b) { asm volatile("bar.sync %0, 352;" ::"r"(7 + b) : "memory"); }
+__device__ __forceinline__ void bar_lfree_arrive(int b) { asm volatile("bar.arrive %0, 352;" ::"r"(11 + b) : "memory"); }
+__device__ __forceinline__ void bar_lfree_sync(int b) { asm volatile("bar.sync %0, 352;" ::"r"(11 + b) : "memory"); }
+// Accumulator tile t is handed back to the MMA warp through hardware named barrier 2+t (4 consumer warps arrive, the
+// MMA warp syncs: 160 threads): the wake-up is immediate, unlike polling an mbarrier from the issuing thread.
+__device__ __forceinline__ void bar_tile_arrive(int t) { asm volatile("bar.arrive %0, 288;" ::"r"(2 + t) : "memory"); }
+__device__ __forceinline__ void bar_tile_sync(int t) { asm volatile("bar.sync %0, 288;" ::"r"(2 + t) : "memory"); }
+
+// shared-memory matrix descriptor, no swizzle, K-major: LBO = byte stride between core matrices along K,
+// SBO = byte stride between 8-row groups along N (validated by tools/tc_probe.cu)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t) ((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t) ((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t) ((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t) 1 << 46;
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, dense
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) { return (1u << 4) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24); }
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, uint32_t r0, uint32_t r1)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- staging + conversion (converter warps) ----------------------------------------------------------------------
+// The raw interleaved bytes [x0*CH-16, x0*CH+(MW+4)*CH) of the 8 rows of a group are copied global -> shared with
+// 16-byte cp.async two groups ahead of their conversion (x0*CH is 16-byte aligned: x0 is a multiple of 128).
+// Chunks outside [0, pitch) are skipped: clamped pixel indices never read them.
+// The chunk -> (row, byte offset) mapping of a converter thread is the same for every group of an item: it is computed
+// once (StageMap) and a group costs one row-pointer lookup and one cp.async per chunk.
+template <int CH>
+struct StageMap {
+    static constexpr int CHUNKS = RawGeom<CH>::CHUNKS;
+    static constexpr int PER = (8 * CHUNKS + NCONV - 1) / NCONV;   // chunks per thread (CH=3: 3, CH=1: 1)
+    int ly[PER];          // row of the group, -1: no copy
+    int soff[PER];        // byte offset inside a raw buffer
+    long long gb[PER];    // byte offset inside the image row
+    __device__ __forceinline__ void init(const DctcK1Args& a, int x0, int ct)
+    {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int c = ct + i * NCONV;
+            const int r = c / CHUNKS, k = c - r * CHUNKS;
+            gb[i] = (long long) x0 * CH - 16 + 16 * k;
+            soff[i] = r * RawGeom<CH>::ROW + 16 * k;
+            ly[i] = (c < 8 * CHUNKS && gb[i] >= 0 && gb[i] + 16 <= (long long) a.pitch) ? r : -1;
+        }
+    }
+    __device__ __forceinline__ void stage(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R, int vy0) const
+    {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            if (ly[i] >= 0) {
+                const uint8_t* src = dctc_row_ptr(a, img, vy0 + ly[i]) + gb[i];
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(R + soff[i])), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+};
+
+// Luma in this kernel is the EXACT integer 2126 R + 7152 G + 722 B (= 10000 * 255 * liblqr's LQR_ER_LUMA value, below
+// 2^22, so its float is exact too); grey is 10000 * v.  Two u8 dot products per pixel (coefficients split into a high
+// and a low byte) replace three byte->float conversions and an FMA chain.  The factor 2^-13 of the scaled x-pass
+// (fp16 range of the hi/lo operands) and the 1/10000 are folded into the final weight.
+constexpr float LUMA_WEIGHT_SCALE = 8192.0f / 10000.0f;
+
+template <int CH>
+__device__ __forceinline__ float luma_raw(const uint8_t* __restrict__ p)
+{
+    if (CH == 3) return (float) (2126u * p[0] + 7152u * p[1] + 722u * p[2]);
+    return (float) (10000u * p[0]);
+}
+
+// luma of four consecutive pixels from their CH*4 raw bytes (4-byte aligned); same values as luma_raw
+template <int CH>
+__device__ __forceinline__ void quad_luma(const uint8_t* __restrict__ p, float (&l)[4])
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    if (CH == 3) {
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        constexpr uint32_t CLO = 0x00D2F04Eu, CHI = 0x00021B08u;   // (78, 240, 210, 0), (8, 27, 2, 0): 2126, 7152, 722
+        const uint32_t p1 = __byte_perm(w0, w1, 0x6543), p2 = __byte_perm(w1, w2, 0x5432);
+        l[0] = (float) __dp4a(w0, CLO, __dp4a(w0, CHI, 0u) << 8);
+        l[1] = (float) __dp4a(p1, CLO, __dp4a(p1, CHI, 0u) << 8);
+        l[2] = (float) __dp4a(p2, CLO, __dp4a(p2, CHI, 0u) << 8);
+        l[3] = (float) __dp4a(w2, CLO << 8, __dp4a(w2, CHI << 8, 0u) << 8);
+    } else {
+        const uint32_t w0 = w[0];
+#pragma unroll
+        for (int i = 0; i < 4; i++) l[i] = (float) (10000u * ((w0 >> (8 * i)) & 255u));
+    }
+}
+
+// dctc_dct_fwd2<8> (tools/gen_dct.py) with every constant scaled by 2^-13 (exact), so that the x-pass coefficients of
+// integer luma values up to 2.55e6 stay inside the fp16 range of the hi/lo operand split
+__device__ __forceinline__ void dct8_fwd2_scaled(const float2* __restrict__ v, float2* __restrict__ X)
+{
+    constexpr float S = 1.0f / 8192.0f;
+    const float2 t1 = dctc_f2add(v[0], v[7]), t2 = dctc_f2sub(v[0], v[7]);
+    const float2 t3 = dctc_f2add(v[1], v[6]), t4 = dctc_f2sub(v[1], v[6]);
+    const float2 t5 = dctc_f2add(v[2], v[5]), t6 = dctc_f2sub(v[2], v[5]);
+    const float2 t7 = dctc_f2add(v[3], v[4]), t8 = dctc_f2sub(v[3], v[4]);
+    X[1] = dctc_f2fma(S * 9.754516184e-02f, t8, dctc_f2fma(S * 2.777851224e-01f, t6, dctc_f2fma(S * 4.157347977e-01f, t4, dctc_f2mul(S * 4.903926253e-01f, t2))));
+    X[3] = dctc_f2fma(S * -2.777851224e-01f, t8, dctc_f2fma(S * -4.903926253e-01f, t6, dctc_f2fma(S * -9.754516184e-02f, t4, dctc_f2mul(S * 4.157347977e-01f, t2))));
+    X[5] = dctc_f2fma(S * 4.157347977e-01f, t8, dctc_f2fma(S * 9.754516184e-02f, t6, dctc_f2fma(S * -4.903926253e-01f, t4, dctc_f2mul(S * 2.777851224e-01f, t2))));
+    X[7] = dctc_f2fma(S * -4.903926253e-01f, t8, dctc_f2fma(S * 4.157347977e-01f, t6, dctc_f2fma(S * -2.777851224e-01f, t4, dctc_f2mul(S * 9.754516184e-02f, t2))));
+    const float2 t9 = dctc_f2add(t1, t7), t10 = dctc_f2sub(t1, t7);
+    const float2 t11 = dctc_f2add(t3, t5), t12 = dctc_f2sub(t3, t5);
+    X[2] = dctc_f2fma(S * 1.913417131e-01f, t12, dctc_f2mul(S * 4.619397521e-01f, t10));
+    X[6] = dctc_f2fma(S * -4.619397521e-01f, t12, dctc_f2mul(S * 1.913417131e-01f, t10));
+    const float2 t13 = dctc_f2add(t9, t11), t14 = dctc_f2sub(t9, t11);
+    X[4] = dctc_f2mul(S * 3.535533845e-01f, t14);
+    X[0] = dctc_f2mul(S * 3.535533845e-01f, t13);
+}
+
+// raw rows -> luma row pairs; staged index i <-> image column clamp(x0 - 4 + i) (src/render.c:122-132).
+// A task is one 4-pixel group of one row pair (4 x 34 tasks per group of rows); a converter thread owns the same one or
+// two tasks for every group of an item, so their offsets and the border test are computed once per item (ConvMap).
+// Groups that touch the image border take the per-pixel clamped path.
+template <int CH>
+struct ConvMap {
+    static constexpr int ROW = RawGeom<CH>::ROW;
+    static constexpr int PER = (4 * NQUAD + NCONV - 1) / NCONV;   // 2
+    int roff[PER];     // byte offset of the task's first raw row inside a raw buffer, -1: no task
+    int loff[PER];     // float2 index inside a luma buffer
+    int gx[PER];       // image column of the first pixel; INT_MIN when the four pixels are all inside the image
+    __device__ __forceinline__ void init(const DctcK1Args& a, int x0, int ct)
+    {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int task = ct + i * NCONV;
+            const int p = task / NQUAD, q = task - p * NQUAD - 1;   // row pair 0..3, quad -1..32
+            const int g = x0 + 4 * q;
+            roff[i] = task < 4 * NQUAD ? (2 * p) * ROW + 16 + 4 * CH * q : -1;
+            loff[i] = p * LWP + 4 * q + 4;
+            gx[i] = (g >= 0 && g + 3 < a.w) ? (int) 0x80000000 : g;
+        }
+    }
+    __device__ __forceinline__ void convert(const DctcK1Args& a, const uint8_t* __restrict__ R, float2* __restrict__ L) const
+    {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            if (roff[i] < 0) continue;
+            const uint8_t* r0 = R + roff[i];
+            const uint8_t* r1 = r0 + ROW;
+            float l0[4], l1[4];
+            if (gx[i] == (int) 0x80000000) {
+                quad_luma<CH>(r0, l0);
+                quad_luma<CH>(r1, l1);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int off = (max(0, min(gx[i] + k, a.w - 1)) - gx[i]) * CH;
+                    l0[k] = luma_raw<CH>(r0 + off);
+                    l1[k] = luma_raw<CH>(r1 + off);
+                }
+            }
+            float4* dst = reinterpret_cast<float4*>(L + loff[i]);
+            dst[0] = make_float4(l0[0], l1[0], l0[1], l1[1]);
+            dst[1] = make_float4(l0[2], l1[2], l0[3], l1[3]);
+        }
+    }
+};
+
+// H -> fp16 hi and fp16 MINUS lo for two vertically adjacent rows (low half = even row = even K index).
+// hi = rn16(H); the residual comes from one mixed-precision subtract per value (sub.f32.f16 = FHADD: hi - H, exact),
+// so no half->float conversion is needed; the sign is undone by the negate-A bit of the lo*Bh MMA's descriptor.
+__device__ __forceinline__ void split_pair(float2 x, uint32_t& hi, uint32_t& nlo)
+{
+    const __half2 h = __floats2half2_rn(x.x, x.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const uint16_t h0 = (uint16_t) (hi & 0xffffu), h1 = (uint16_t) (hi >> 16);
+    float r0, r1;
+    asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(r0) : "h"(h0), "f"(x.x));
+    asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(r1) : "h"(h1), "f"(x.y));
+    const __half2 l = __floats2half2_rn(r0, r1);
+    nlo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// x-pass + split + tcgen05.st of half a group (warps 0-3: row pairs 0,1; warps 4-7: row pairs 2,3) into ring position
+// g % 3 (and into position 3 as well when g % 3 == 0); arrives on the "operands stored" barrier
+__device__ __forceinline__ void produce_group(TcSmem& s, int g, int px, int half, uint32_t tmem_lane, long long* g_tt_acc)
+{
+    (void) g_tt_acc;
+    const int pos = g % 3;
+    const uint32_t ta = tmem_lane + TM_A + (uint32_t) (pos * 4 + half * 2);
+    const float2 (*Lg)[LWP] = s.L[g & 1];
+    uint32_t hi[8][2], lo[8][2];
+#pragma unroll
+    for (int pp = 0; pp < 2; pp++) {
+        float2 v[8], X[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = Lg[2 * half + pp][px + j + 1];
+        if (pp == 1) bar_lfree_arrive(g & 1);   // last read of this luma buffer
+        dct8_fwd2_scaled(v, X);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) split_pair(X[k1], hi[k1][pp], lo[k1][pp]);
+    }
+    // position g % 3 still holds group g-3, last read (as the older group) by the MMAs of step g-3
+    if (g >= 3) {
+        TT_T0();
+        mbar_wait(smem_u32(&s.bar_a_free[pos]), (uint32_t) ((g / 3 - 1) & 1));
+        TT_ACC(0, 1);
+        tc_fence_after();
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 8; k1++) {
+        tmem_st_x2(ta + (uint32_t) (k1 * 32), hi[k1][0], hi[k1][1]);
+        tmem_st_x2(ta + (uint32_t) (k1 * 32 + 16), lo[k1][0], lo[k1][1]);
+    }
+    if (pos == 0) {   // the copy that makes (position 2, position 0) contiguous
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) {
+            tmem_st_x2(ta + (uint32_t) (k1 * 32 + 12), hi[k1][0], hi[k1][1]);
+            tmem_st_x2(ta + (uint32_t) (k1 * 32 + 28), lo[k1][0], lo[k1][1]);
+        }
+    }
+    {
+        TT_T0();
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // warp-wide: every lane's stores have completed
+        TT_ACC(0, 2);
+    }
+    tc_fence_before();
+    // Group 0 is not announced on its own: the arrival of group 1 covers both (same warp, program order).
+    if (g >= 1) bar_afull_arrive();
+}
+
+// ---- consumer fold -------------------------------------------------------------------------------------------
+// A consumer warp folds 4 rows (half a tile) of every second k1 (even k1: sets 0,1; odd k1: sets 2,3).  The odd sets
+// park their partial results, the even sets combine and store.  Class rule (edges != textures) as in DctcTracker:
+// A = |T[0][1]| and M = max|T[0][2..]| come from the k1 = 0 tile (even sets), Bv = |T[1][0]| from the k1 = 1 tile (odd
+// sets), Z is the maximum of everything else.
+template <bool UNIFORM>
+struct TcFold {
+    float z[NR];          // running maximum (UNIFORM: of every coefficient but T[0][0])
+    float a[NR], mm[NR];  // even sets, non-uniform only
+    float bv[NR];         // odd sets, non-uniform only
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int i = 0; i < NR; i++) { z[i] = 0.0f; a[i] = 0.0f; mm[i] = -1.0f; bv[i] = 0.0f; }
+    }
+    template <int K1>
+    __device__ __forceinline__ void add(const uint32_t (&v)[32])
+    {
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            if (UNIFORM) {
+                float t = z[i];
+                if (K1 != 0) t = fmaxf(t, fabsf(__uint_as_float(v[i * 8])));   // (0,0) is skipped (src/dct.c:101)
+                t = fmaxf(t, fabsf(__uint_as_float(v[i * 8 + 1])));
+#pragma unroll
+                for (int k2 = 2; k2 < 8; k2 += 2)
+                    t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[i * 8 + k2])), fabsf(__uint_as_float(v[i * 8 + k2 + 1]))));
+                z[i] = t;
+            } else if (K1 == 0) {
+                a[i] = fabsf(__uint_as_float(v[i * 8 + 1]));
+#pragma unroll
+                for (int k2 = 2; k2 < 8; k2++) mm[i] = fmaxf(mm[i], fabsf(__uint_as_float(v[i * 8 + k2])));
+            } else {
+                if (K1 == 1) bv[i] = fabsf(__uint_as_float(v[i * 8]));
+                else z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[i * 8])));
+#pragma unroll
+                for (int k2 = 1; k2 < 8; k2++) z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[i * 8 + k2])));
+            }
+        }
+    }
+    // odd set: park the partial results (pk = this thread's column of park[parity][half])
+    __device__ __forceinline__ void park(float* pk) const
+    {
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            pk[i * MW] = z[i];
+            if (!UNIFORM) pk[(NR + i) * MW] = bv[i];
+        }
+    }
+    // even set: combine with the parked partial results of the odd set
+    __device__ __forceinline__ float result(int i, const float* pk, float we, float wt) const
+    {
+        const float zz = fmaxf(z[i], pk[i * MW]);
+        if (UNIFORM) return zz * wt;
+        const float b = pk[(NR + i) * MW];
+        const float am = fmaxf(a[i], mm[i]);
+        const float top = fmaxf(fmaxf(am, b), zz);
+        const bool tex = (zz >= fmaxf(am, b)) || (!(b >= am) && (mm[i] >= a[i]));
+        return top * (tex ? wt : we);
+    }
+};
+
+template <int K1, bool UNIFORM>
+__device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32_t tmem_lane, uint32_t half, long long* g_tt_acc)
+{
+    (void) g_tt_acc;
+    constexpr int t = K1 & 3;                 // accumulator tile; used twice per step (k1 = t and t + 4)
+    {
+        TT_T0();
+        mbar_wait(smem_u32(&s.bar_d_full[t]), (uint32_t) ((K1 >> 2) & 1));
+        TT_ACC(1, K1 == 0 ? 0 : 1);
+    }
+    tc_fence_after();
+    uint32_t v[32];
+    {
+        TT_T0();
+        tmem_ld_x32(tmem_lane + TM_D + 64u * t + 32u * half, v);   // this warp's half of the tile: rows 4*half .. 4*half+3
+        TT_ACC(1, 2);
+    }
+    tc_fence_before();
+    bar_tile_arrive(t);
+    f.template add<K1>(v);
+}
+
+// Persistent kernel: ONE CTA per SM (all 512 TMEM columns), work items = (frame, segment, strip) handed out by an atomic
+// counter.  warps 0-7 producers (lane quarter = warp % 4; warps 0-3 rows 0-3 of a group, warps 4-7 rows 4-7), warps 8-15
+// consumers in four sets of four warps (set = even/odd k1 x rows 0-3 / 4-7 of the tile: four tiles in flight), warp 24
+// MMA issuer, warps 25-27 converters.  Launched with 72 registers; setmaxnreg: producers 96, consumers 56, MMA + converters 40.
+template <bool UNIFORM, int CH>
+__global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc8w_kernel(const DctcK1Args a, int seg_rows, int strips, int segs, int n_items,
+                                                                     int* __restrict__ counter)
+{
+    __shared__ TcSmem s;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
+
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // Toeplitz operands: Tz[n = i*8 + k2][k] = B8[k2][k - i]; the older group always sits in the lower columns of the
+    // A operand, so one K order serves every step
+    {
+        uint16_t* Bq = reinterpret_cast<uint16_t*>(&s.B[0][0]);
+        for (int idx = tid; idx < 2 * 1024; idx += NTHREADS) {
+            const int v = idx >> 10, n = (idx >> 4) & 63, k = idx & 15;
+            const int i = n >> 3, k2 = n & 7;
+            const int c = k - i;
+            const uint16_t val = (c >= 0 && c < 8) ? DCTC_TC_BASIS8[v][k2 * 8 + c] : (uint16_t) 0;
+            Bq[v * 1024 + (n >> 3) * 128 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7)] = val;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t lane_off = (uint32_t) ((warp & 3) * 32) << 16;
+
+    auto begin_item = [&](bool first) -> int {
+        if (tid == 0) {
+            s.work = atomicAdd(counter, 1);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                if (!first) mbar_inval(smem_u32(&s.bar_a_free[i]));
+                mbar_init(smem_u32(&s.bar_a_free[i]), 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (!first) mbar_inval(smem_u32(&s.bar_d_full[i]));
+                mbar_init(smem_u32(&s.bar_d_full[i]), 1);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        return s.work;
+    };
+    auto end_item = [&]() {
+        tc_fence_before();
+        __syncthreads();    // every role is done with the barriers, TMEM and staging buffers of this item
+    };
+#define DCTC_ITEM_LOOP                                                                                                 \
+    for (bool first = true;; first = false) {                                                                          \
+        const int item = begin_item(first);                                                                            \
+        if (item >= n_items) break;                                                                                    \
+        const uint32_t tmem = s.tmem_base;                                                                             \
+        const uint32_t tmem_lane = tmem + lane_off;                                                                    \
+        const int strip = item % strips;                                                                               \
+        const int rest = item / strips;                                                                                \
+        const int seg = rest % segs, frame = rest / segs;                                                              \
+        const int x0 = strip * MW;                                                                                     \
+        const int y0 = seg * seg_rows;                                                                                 \
+        const int y1 = min(y0 + seg_rows, a.h);                                                                        \
+        const int nsteps = (y1 - y0 + 7) >> 3;                                                                         \
+        const uint8_t* __restrict__ img = a.img + (size_t) frame * a.frame_stride;                                     \
+        float* __restrict__ out = a.out + (size_t) frame * a.out_frame_stride;                                         \
+        (void) tmem; (void) tmem_lane; (void) x0; (void) y1; (void) img; (void) out;
+
+    TT_DECL();
+    if (warp < 8) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        DCTC_ITEM_LOOP
+        // ===== producers: group g = virtual rows y0-3+8g .. y0+4+8g; step j consumes groups j and j+1 =====
+        const int px = tid & 127, half = warp >> 2;
+        for (int g = 0; g <= nsteps; g++) {
+            {
+                TT_T0();
+                bar_lfull_sync(g & 1);                        // the converters have written luma buffer g&1
+                TT_ACC(0, 0);
+            }
+            produce_group(s, g, px, half, tmem_lane, g_tt_acc);
+        }
+        end_item();
+        }
+        TT_REPORT(0, tid == 0);
+    } else if (warp < WARP_MMA) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        DCTC_ITEM_LOOP
+        // ===== consumers: set = (warp - 8) / 4; bit 0 = tile half (rows 0-3 / 4-7), bit 1 = odd k1 =====
+        const int cset = (warp - 8) >> 2;
+        const uint32_t half = (uint32_t) (cset & 1);
+        const bool odd = (cset & 2) != 0;
+        const int px = tid & 127;
+        const int gx = x0 + px;
+        const float we = a.w_edges * LUMA_WEIGHT_SCALE, wt = a.w_textures * LUMA_WEIGHT_SCALE;
+        for (int st = 0; st < nsteps; st++) {
+            TcFold<UNIFORM> f;
+            f.init();
+            float* pk = &s.park[st & 1][half][0][px];
+            bar_step_sync();                                  // the MMA warp has started this step
+            if (!odd) {
+                consume_k1<0, UNIFORM>(s, f, tmem_lane, half, g_tt_acc);
+                consume_k1<2, UNIFORM>(s, f, tmem_lane, half, g_tt_acc);
+                consume_k1<4, UNIFORM>(s, f, tmem_lane, half, g_tt_acc);
+                consume_k1<6, UNIFORM>(s, f, tmem_lane, half, g_tt_acc);
+                bar_pair_sync((int) half);                    // the odd set has parked its partial results
+                const int gy = y0 + 8 * st + NR * (int) half;
+                if (gx < a.w) {
+                    float* __restrict__ o = out + (size_t) gy * a.out_pitch + gx;
+#pragma unroll
+                    for (int i = 0; i < NR; i++)
+                        if (gy + i < y1) o[(size_t) i * a.out_pitch] = f.result(i, pk, we, wt);
+                }
+            } else {
+                consume_k1<1, UNIFORM>(s, f, tmem_lane, half, g_tt_acc);
+                consume_k1<3, UNIFORM>(s, f, tmem_lane, half, g_tt_acc);
+                consume_k1<5, UNIFORM>(s, f, tmem_lane, half, g_tt_acc);
+                consume_k1<7, UNIFORM>(s, f, tmem_lane, half, g_tt_acc);
+                f.park(pk);
+                bar_pair_arrive((int) half);
+            }
+        }
+        end_item();
+        }
+        TT_REPORT(1, tid == 256);
+    } else if (warp == WARP_MMA) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        DCTC_ITEM_LOOP
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc(128, 64);
+        const uint64_t bh = make_smem_desc(smem_u32(&s.B[0][0]), 128, 256);
+        const uint64_t bl = bh + 128;                         // each operand copy is 2048 bytes = 128 descriptor units
+        for (int st = 0; st < nsteps; st++) {
+            {
+                TT_T0();
+                bar_afull_sync();                             // groups st and st+1 are in TMEM
+                TT_ACC(2, 0);
+            }
+            tc_fence_after();
+            bar_step_arrive();                                // wakes the consumers of this step
+            const uint32_t apos = (uint32_t) (st % 3) * 4u;   // the older group's position; the newer one follows it
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++) {
+                const int t = k1 & 3;
+                if (st > 0 || k1 >= 4) {
+                    TT_T0();
+                    bar_tile_sync(t);                         // the consumers have loaded the previous contents of tile t
+                    TT_ACC(2, 1);
+                }
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d = tmem + TM_D + 64u * t;
+                    const uint32_t ah = tmem + TM_A + (uint32_t) k1 * 32u + apos, al = ah + 16u;
+                    mma_ts(d, ah, bh, idesc, 0u);
+                    mma_ts(d, al, bh, idesc | (1u << 13), 1u);   // A negated: the ring holds -lo
+                    mma_ts(d, ah, bl, idesc, 1u);
+                    mma_commit(smem_u32(&s.bar_d_full[t]));
+                    // position st % 3 (group st, the older one of this step) is free once this step's MMAs are done
+                    if (k1 == 7 && st + 3 <= nsteps) mma_commit(smem_u32(&s.bar_a_free[st % 3]));
+                }
+                __syncwarp();
+            }
+        }
+        // the last use of each tile was arrived on but never waited for: drain the named barriers so that their
+        // generations start clean for the next work item
+        bar_tile_sync(0);
+        bar_tile_sync(1);
+        bar_tile_sync(2);
+        bar_tile_sync(3);
+        end_item();
+        }
+        TT_REPORT(2, tid == 32 * WARP_MMA);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        DCTC_ITEM_LOOP
+        // ===== converters: raw rows of group g+2 in flight while group g is converted =====
+        const int ct = tid - (NTHREADS - NCONV);
+        StageMap<CH> sm;
+        sm.init(a, x0, ct);
+        ConvMap<CH> cm;
+        cm.init(a, x0, ct);
+        sm.stage(a, img, s.Raw[0], y0 - 3);
+        sm.stage(a, img, s.Raw[1], y0 + 5);
+        int slot = 0;                                         // raw buffer of group g (g % 3)
+        for (int g = 0; g <= nsteps; g++) {
+            {
+                TT_T0();
+                asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of group g have landed
+                TT_ACC(3, 0);
+            }
+            {
+                TT_T0();
+                bar_converters();                             // ... everybody's; raw buffer (g+2)%3 = (g-1)%3 is free
+                TT_ACC(3, 1);
+            }
+            if (g >= 2) {
+                TT_T0();
+                bar_lfree_sync(g & 1);                        // the producers have read group g-2 out of this buffer
+                TT_ACC(3, 2);
+            }
+            cm.convert(a, s.Raw[slot], &s.L[g & 1][0][0]);
+            bar_lfull_arrive(g & 1);
+            const int nslot = slot == 0 ? 2 : slot - 1;       // (g + 2) % 3
+            if (g + 2 <= nsteps) sm.stage(a, img, s.Raw[nslot], y0 - 3 + 8 * (g + 2));
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            slot = slot == 2 ? 0 : slot + 1;
+        }
+        // the last two groups' "free" arrivals were never waited for: drain them so the next item starts clean
+        bar_lfree_sync((nsteps - 1) & 1);
+        bar_lfree_sync(nsteps & 1);
+        end_item();
+        }
+        TT_REPORT(3, tid == 32 * WARP_MMA + 32);
+    }
+#undef DCTC_ITEM_LOOP
+
+    if (warp == WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "r"(TMEM_COLS));
+}
+
+}  // namespace
+
+// Same contract as dctc_launch_k1_tc8 (cudaErrorNotSupported outside the fast path).
+cudaError_t dctc_launch_k1_tc8w(const DctcK1Args& a, int n_frames, bool uniform, int* counter, int sm_count, cudaStream_t stream)
+{
+    if (a.w <= 0 || a.h <= 0 || n_frames <= 0) return cudaSuccess;
+    if (a.seam) return cudaErrorInvalidValue;  // band mode lives in the tile kernel
+    auto aligned16 = [](const void* p, size_t pitch) { return (((uintptr_t) p | pitch) & 15) == 0; };
+    const bool fast = (a.channels == 3 || a.channels == 1) && aligned16(a.img, a.pitch) && (a.frame_stride & 15) == 0 &&
+                      (!a.top || aligned16(a.top, a.top_pitch)) && (!a.bot || aligned16(a.bot, a.bot_pitch));
+    if (!fast || !counter) return cudaErrorNotSupported;
+    const int strips = (a.w + MW - 1) / MW;
+    int seg = 512;
+    while (seg > 32 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 12LL * sm_count) seg >>= 1;
+    const int segs = (a.h + seg - 1) / seg;
+    const long long items = (long long) strips * segs * n_frames;
+    if (items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const int grid = (int) (items < (long long) sm_count ? items : (long long) sm_count);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+#define DCTC_TCW_LAUNCH(U, C)                                                                                          \
+    do {                                                                                                               \
+        cudaError_t ea = cudaFuncSetAttribute(dctc_k1_tc8w_kernel<U, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAD_SMEM); \
+        if (ea != cudaSuccess) return ea;                                                                              \
+        dctc_k1_tc8w_kernel<U, C><<<grid, NTHREADS, PAD_SMEM, stream>>>(a, seg, strips, segs, (int) items, counter);   \
+    } while (0)
+    if (a.channels == 3) { if (uniform) DCTC_TCW_LAUNCH(true, 3); else DCTC_TCW_LAUNCH(false, 3); }
+    else { if (uniform) DCTC_TCW_LAUNCH(true, 1); else DCTC_TCW_LAUNCH(false, 1); }
+#undef DCTC_TCW_LAUNCH
+    return cudaGetLastError();
+}
