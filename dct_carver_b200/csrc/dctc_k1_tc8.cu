@@ -187,32 +187,41 @@ template <int CH>
 struct StageMap {
     static constexpr int CHUNKS = RawGeom<CH>::CHUNKS;
     static constexpr int PER = (8 * CHUNKS + NCONV - 1) / NCONV;   // chunks per thread (CH=3: 3, CH=1: 1)
-    int ly[PER];          // row of the group, -1: no copy
-    int soff[PER];        // byte offset inside a raw buffer
-    long long gb[PER];    // byte offset inside the image row
+    int ly[PER];               // row of the group, -1: no copy
+    int soff[PER];             // byte offset inside a raw buffer
+    const uint8_t* src[PER];   // source of the chunk in the group staged last
+    int last_vy0;              // first virtual row of that group; INT_MIN: none yet
     __device__ __forceinline__ void init(const DctcK1Args& a, int x0, int ct)
     {
 #pragma unroll
         for (int i = 0; i < PER; i++) {
             const int c = ct + i * NCONV;
             const int r = c / CHUNKS, k = c - r * CHUNKS;
-            gb[i] = (long long) x0 * CH - 16 + 16 * k;
+            const long long gb = (long long) x0 * CH - 16 + 16 * k;
             soff[i] = r * RawGeom<CH>::ROW + 16 * k;
-            ly[i] = (c < 8 * CHUNKS && gb[i] >= 0 && gb[i] + 16 <= (long long) a.pitch) ? r : -1;
+            ly[i] = (c < 8 * CHUNKS && gb >= 0 && gb + 16 <= (long long) a.pitch) ? r : -1;
+            src[i] = nullptr;
         }
+        last_vy0 = (int) 0x80000000;
     }
-    __device__ __forceinline__ void stage(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R, int vy0) const
+    // Groups advance by 8 rows: while a group and its predecessor lie inside the band itself (no halo rows, no edge
+    // replication) the source pointers just move by 8 pitches; otherwise they are looked up row by row.
+    __device__ __forceinline__ void stage(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R, int vy0, int x0)
     {
+        const bool step8 = vy0 == last_vy0 + 8 && last_vy0 >= 0 && vy0 + 7 < a.h;
 #pragma unroll
         for (int i = 0; i < PER; i++) {
             if (ly[i] >= 0) {
-                const uint8_t* src = dctc_row_ptr(a, img, vy0 + ly[i]) + gb[i];
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(R + soff[i])), "l"(src) : "memory");
+                if (step8) src[i] += 8 * a.pitch;
+                else src[i] = dctc_row_ptr(a, img, vy0 + ly[i]) + ((long long) x0 * CH - 16 + (soff[i] - ly[i] * RawGeom<CH>::ROW));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(R + soff[i])), "l"(src[i]) : "memory");
             }
         }
+        last_vy0 = vy0;
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 };
+
 
 // Luma in this kernel is the EXACT integer 2126 R + 7152 G + 722 B (= 10000 * 255 * liblqr's LQR_ER_LUMA value, below
 // 2^22, so its float is exact too); grey is 10000 * v.  Two u8 dot products per pixel (coefficients split into a high
@@ -660,8 +669,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         sm.init(a, x0, ct);
         ConvMap<CH> cm;
         cm.init(a, x0, ct);
-        sm.stage(a, img, s.Raw[0], y0 - 3);
-        sm.stage(a, img, s.Raw[1], y0 + 5);
+        sm.stage(a, img, s.Raw[0], y0 - 3, x0);
+        sm.stage(a, img, s.Raw[1], y0 + 5, x0);
         int slot = 0;                                         // raw buffer of group g (g % 3)
         for (int g = 0; g <= nsteps; g++) {
             {
@@ -682,7 +691,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
             cm.convert(a, s.Raw[slot], &s.L[g & 1][0][0]);
             bar_lfull_arrive(g & 1);
             const int nslot = slot == 0 ? 2 : slot - 1;       // (g + 2) % 3
-            if (g + 2 <= nsteps) sm.stage(a, img, s.Raw[nslot], y0 - 3 + 8 * (g + 2));
+            if (g + 2 <= nsteps) sm.stage(a, img, s.Raw[nslot], y0 - 3 + 8 * (g + 2), x0);
             else asm volatile("cp.async.commit_group;" ::: "memory");
             slot = slot == 2 ? 0 : slot + 1;
         }
