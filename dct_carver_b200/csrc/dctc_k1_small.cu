@@ -127,6 +127,45 @@ __device__ __forceinline__ void stage_raw_async(const DctcK1Args& a, const uint8
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// The chunk -> (row, byte offset) mapping of a thread is the same for every 8-row chunk of a segment: it is computed
+// once, and while consecutive chunks lie inside the band itself (no halo rows, no edge replication) the source pointers
+// just advance by 8 pitches instead of being looked up row by row.
+template <int CH, int B>
+struct StageMap {
+    using G = RawGeom<CH, B>;
+    int ly[G::PER];              // row of the chunk, -1: no copy
+    int soff[G::PER];            // byte offset inside a raw buffer
+    const uint8_t* src[G::PER];
+    int last_vy0;
+    __device__ __forceinline__ void init(const DctcK1Args& a, int x0, int tid)
+    {
+#pragma unroll
+        for (int i = 0; i < G::PER; i++) {
+            const int c = tid + i * MW;
+            const int r = c / G::CHUNKS, k = c - r * G::CHUNKS;
+            const long long gb = (long long) x0 * CH - 16 + 16 * k;
+            soff[i] = r * G::ROW + 16 * k;
+            ly[i] = (c < 8 * G::CHUNKS && gb >= 0 && gb + 16 <= (long long) a.pitch) ? r : -1;
+            src[i] = nullptr;
+        }
+        last_vy0 = (int) 0x80000000;
+    }
+    __device__ __forceinline__ void stage(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R, int vy0, int x0)
+    {
+        const bool step8 = vy0 == last_vy0 + 8 && last_vy0 >= 0 && vy0 + 7 < a.h;
+#pragma unroll
+        for (int i = 0; i < G::PER; i++) {
+            if (ly[i] >= 0) {
+                if (step8) src[i] += 8 * a.pitch;
+                else src[i] = dctc_row_ptr(a, img, vy0 + ly[i]) + ((long long) x0 * CH - 16 + (soff[i] - ly[i] * G::ROW));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(R + soff[i])), "l"(src[i]) : "memory");
+            }
+        }
+        last_vy0 = vy0;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+};
+
 template <int CH>
 __device__ __forceinline__ float luma_raw(const uint8_t* __restrict__ p)
 {
@@ -266,8 +305,10 @@ __global__ void __launch_bounds__(MW, B == 2 ? 8 : 6) dctc_k1_small_kernel(const
     // which feed output rows y0+8(c-1) .. +7.  Raw buffers rotate over three slots (two chunks in flight).
     const int nchunks = 1 + (y1 - y0 + 7) / 8;
     stage_raw_async<CH, B, B - 1>(a, img, Raw[0], y0 - R0, x0, tid);    // the prologue needs B-1 rows only
-    stage_raw_async<CH, B>(a, img, Raw[1], y0 + R1, x0, tid);
-    if (nchunks > 2) stage_raw_async<CH, B>(a, img, Raw[2], y0 + R1 + 8, x0, tid);
+    StageMap<CH, B> sm;
+    sm.init(a, x0, tid);
+    sm.stage(a, img, Raw[1], y0 + R1, x0);
+    if (nchunks > 2) sm.stage(a, img, Raw[2], y0 + R1 + 8, x0);
     else asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncthreads();
@@ -287,7 +328,7 @@ __global__ void __launch_bounds__(MW, B == 2 ? 8 : 6) dctc_k1_small_kernel(const
         __syncthreads();                                        // ... everybody's; L[c&1] and the raw buffer of chunk c-1 are free
         // refill the raw buffer chunk c-1 sat in with chunk c+2
         const int fslot = slot == 0 ? 2 : slot - 1;
-        if (c + 2 < nchunks) stage_raw_async<CH, B>(a, img, Raw[fslot], y0 + R1 + 8 * (c + 1), x0, tid);
+        if (c + 2 < nchunks) sm.stage(a, img, Raw[fslot], y0 + R1 + 8 * (c + 1), x0);
         else asm volatile("cp.async.commit_group;" ::: "memory");
         float* Lb = L[c & 1];
         convert_raw<CH, B>(a, Raw[slot], Lb, x0, tid);
