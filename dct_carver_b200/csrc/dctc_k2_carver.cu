@@ -8,6 +8,7 @@
 #include <cuda.h>      // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 #include "dctc_common.cuh"
 #include "dctc_launch.h"
@@ -231,6 +232,16 @@ __device__ __forceinline__ void dp_mbar_wait(uint32_t bar, uint32_t parity)
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N - 1>)
+template <int N, int I = 0, typename F>
+__device__ __forceinline__ void dp_unroll(F&& f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        dp_unroll<N, I + 1>(f);
+    }
+}
+
 // DP_P float4 groups per lane: strip = 128 * DP_P columns, 128 * DP_P - 2 * DP_R of them published.
 // DP_SR: rows per staged chunk of the bulk-copy variant (32 when two stages per warp fit, else 16), 0 = register ring.
 template <int DP_P, int DP_SR>
@@ -350,69 +361,105 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
 #ifdef DCTC_SYNC_DEBUG
     const long long dbg_t0 = clock64();
 #endif
-    float* mrow = mplane + m_pitch;
+    // The row chain is bound by the number of instructions a lone warp per scheduler has to issue (the ncu source view
+    // shows ~6 clk per instruction, mostly fixed-latency "wait" stalls), so the loop body is kept minimal: staged
+    // energies are read with immediate offsets from a shared-space base register, cells outside the image are made
+    // +inf once per chunk in the staged copy (inf + min = inf, no per-row patch), the cumulative plane is written
+    // through one running pointer, and whole blocks run without per-row bounds checks.
+    float* mptr = mplane + m_pitch + c0;             // this lane's first cell of row y
+    unsigned any_mask = 0;
+#pragma unroll
+    for (int g = 0; g < DP_P; g++) any_mask |= inf_mask[g];
     int xb = 0;
     int c_ch = 0, c_st = 0;                          // chunk being consumed, its stage and mbarrier parity
     uint32_t c_par = 0;
-    for (int yb = 1; yb < h; yb += DP_R) {
-        const float* stg = estage;
-#pragma unroll
-        for (int kk = 0; kk < DP_R; kk++) {
-            const int k = kk % PF;
-            const int y = yb + kk;
-            if (TMA && kk % SRD == 0 && y < h) {                          // a new chunk of staged rows starts here
-                dp_mbar_wait(dp_smem_u32(&ebar[tid >> 5][c_st]), c_par);
-                stg = estage + (size_t) c_st * SRD * STRIP + lane * CPL;
-            }
-            if (y < h) {                                                    // uniform across the CTA
-                if (TMA) {
-#pragma unroll
-                    for (int g = 0; g < DP_P; g++) e[0][g] = *reinterpret_cast<const float4*>(stg + (kk % SRD) * STRIP + 4 * g);
-                }
-                // neighbours across lanes; the strip's outermost lanes see +inf (their cells are never published)
-                float l = __shfl_up_sync(0xffffffffu, cur[DP_P - 1].w, 1);
-                float r = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
-                if (lane == 0) l = INF;
-                if (lane == 31) r = INF;
-                float4 o[DP_P];
+    uint32_t stg_s = 0;                              // shared-space address of this lane's cells in the current chunk
+    auto chunk_begin = [&]() {                       // a new chunk of staged rows starts: wait for it, patch its +inf cells
+        dp_mbar_wait(dp_smem_u32(&ebar[tid >> 5][c_st]), c_par);
+        float* sp = estage + (size_t) c_st * SRD * STRIP + lane * CPL;
+        stg_s = dp_smem_u32(sp);
+        if (any_mask) {
+            for (int rr = 0; rr < SRD; rr++) {
 #pragma unroll
                 for (int g = 0; g < DP_P; g++) {
-                    const float lg = g == 0 ? l : cur[g > 0 ? g - 1 : 0].w;
-                    const float rg = g == DP_P - 1 ? r : cur[g < DP_P - 1 ? g + 1 : g].x;
-                    o[g].x = e[k][g].x + fminf(fminf(lg, cur[g].x), cur[g].y);
-                    o[g].y = e[k][g].y + fminf(fminf(cur[g].x, cur[g].y), cur[g].z);
-                    o[g].z = e[k][g].z + fminf(fminf(cur[g].y, cur[g].z), cur[g].w);
-                    o[g].w = e[k][g].w + fminf(fminf(cur[g].z, cur[g].w), rg);
+                    float* q = sp + rr * STRIP + 4 * g;
+                    if (inf_mask[g] & 1u) q[0] = INF;
+                    if (inf_mask[g] & 2u) q[1] = INF;
+                    if (inf_mask[g] & 4u) q[2] = INF;
+                    if (inf_mask[g] & 8u) q[3] = INF;
                 }
-                // refill the ring slot just consumed with the row PF ahead (issued after the last use of the slot, so
-                // the load targets the slot's registers directly; they are not touched again for PF rows)
+            }
+        }
+    };
+    auto chunk_end = [&]() {                         // this warp is done with the chunk: refill its stage nst chunks ahead
+        __syncwarp();
+        if (c_ch + nst < nchunks) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_chunk(c_ch + nst, c_st);
+        }
+        c_ch++;
+        if (++c_st == nst) { c_st = 0; c_par ^= 1u; }
+    };
+    auto row = [&](auto kk_c, int y) {
+        constexpr int kk = decltype(kk_c)::value;
+        constexpr int k = kk % PF;
+        if (TMA) {
+#pragma unroll
+            for (int g = 0; g < DP_P; g++)
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e[0][g].x), "=f"(e[0][g].y), "=f"(e[0][g].z), "=f"(e[0][g].w)
+                             : "r"(stg_s + (uint32_t) (((kk % SRD) * STRIP + 4 * g) * 4)));   // base register + immediate
+        }
+        // neighbours across lanes; the strip's outermost lanes see +inf (their cells are never published)
+        float l = __shfl_up_sync(0xffffffffu, cur[DP_P - 1].w, 1);
+        float r = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
+        if (lane == 0) l = INF;
+        if (lane == 31) r = INF;
+        float4 o[DP_P];
+#pragma unroll
+        for (int g = 0; g < DP_P; g++) {
+            const float lg = g == 0 ? l : cur[g > 0 ? g - 1 : 0].w;
+            const float rg = g == DP_P - 1 ? r : cur[g < DP_P - 1 ? g + 1 : g].x;
+            o[g].x = e[k][g].x + fminf(fminf(lg, cur[g].x), cur[g].y);
+            o[g].y = e[k][g].y + fminf(fminf(cur[g].x, cur[g].y), cur[g].z);
+            o[g].z = e[k][g].z + fminf(fminf(cur[g].y, cur[g].z), cur[g].w);
+            o[g].w = e[k][g].w + fminf(fminf(cur[g].z, cur[g].w), rg);
+        }
+        // register-ring variant: refill the slot just consumed with the row PF ahead (issued after the last use of the
+        // slot, so the load targets the slot's registers directly; they are not touched again for PF rows)
 #if !(DP_EXP & 1)
-                if (!TMA) {
+        if (!TMA) {
 #pragma unroll
-                    for (int g = 0; g < DP_P; g++)
-                        e[k][g] = __ldg(reinterpret_cast<const float4*>(en_g[g] + (size_t) min(y + PF, hm1) * en_pitch));
-                }
+            for (int g = 0; g < DP_P; g++)
+                e[k][g] = __ldg(reinterpret_cast<const float4*>(en_g[g] + (size_t) min(y + PF, hm1) * en_pitch));
+        }
 #endif
 #pragma unroll
-                for (int g = 0; g < DP_P; g++) {
+        for (int g = 0; g < DP_P; g++) {
 #if DP_EXP & 2
-                    if (o[g].x == 12345.678f)
+            if (o[g].x == 12345.678f)
 #endif
-                    if (central && ld_ok[g]) *reinterpret_cast<float4*>(mrow + (c0 + 4 * g)) = o[g];
-                    patch(o[g], inf_mask[g]);                               // cells outside the image stay +inf
-                    cur[g] = o[g];
-                }
-                mrow += m_pitch;
-            }
-            if (TMA && kk % SRD == SRD - 1) {    // this warp is done with the chunk: refill its stage nst chunks ahead
-                __syncwarp();
-                if (c_ch + nst < nchunks) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue_chunk(c_ch + nst, c_st);
-                }
-                c_ch++;
-                if (++c_st == nst) { c_st = 0; c_par ^= 1u; }
-            }
+            if (central && ld_ok[g]) *reinterpret_cast<float4*>(mptr + 4 * g) = o[g];
+            if (!TMA) patch(o[g], inf_mask[g]);      // cells outside the image stay +inf (TMA: their staged energy is +inf)
+            cur[g] = o[g];
+        }
+        mptr += m_pitch;
+    };
+    for (int yb = 1; yb < h; yb += DP_R) {
+        if (yb + DP_R <= h) {                         // whole block: no per-row bounds checks
+            dp_unroll<DP_R>([&](auto kk_c) {
+                constexpr int kk = decltype(kk_c)::value;
+                if (TMA && kk % SRD == 0) chunk_begin();
+                row(kk_c, yb + kk);
+                if (TMA && kk % SRD == SRD - 1) chunk_end();
+            });
+        } else {
+            dp_unroll<DP_R>([&](auto kk_c) {
+                constexpr int kk = decltype(kk_c)::value;
+                const int y = yb + kk;
+                if (TMA && kk % SRD == 0 && y < h) chunk_begin();
+                if (y < h) row(kk_c, y);              // uniform across the CTA
+                if (TMA && kk % SRD == SRD - 1) chunk_end();
+            });
         }
         // exchange the last row of the block: every warp publishes its central cells, then reloads its whole strip
         if (yb + DP_R < h && !(DP_EXP & 4)) {
