@@ -547,7 +547,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
 // MEASURED (1920x1080 noise, 480 seams): the walk recomputes ~150 columns per row on average and needs the full rebuild
 // for 2 of 480 seams, but ONE warp spends ~900 clk per row on it (phases per row: 250-470 clk row arithmetic, ~180 clk
 // side cells + next range, ~340 clk staging; a lone warp has no other warp to hide its 4-6 clk dependent-issue
-// latencies behind), i.e. 918 us per seam against 245 us for the cluster-wide rebuild.  It is therefore OFF by default
+// latencies behind), i.e. 918 us per seam against 199 us for the cluster-wide rebuild.  It is therefore OFF by default
 // (dctc_carver_set_incremental) and kept as the bit-identical reference point for a multi-warp block version.
 #ifndef DCTC_INCR_ABL
 #define DCTC_INCR_ABL 0   // timing ablations only
