@@ -725,7 +725,9 @@ cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, 
     // segment height: long segments amortise the 8-row prologue; keep >= ~6 items per SM so the tail stays short
     int seg = 256;   // (measured on 16 frames of 4K: 1024/512 rows 50.5 us per frame, 256 rows 49.3, 128 rows 50.5, 64 rows 54.7)
     while (seg > 32 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 12LL * sm_count) seg >>= 1;
-    const int segs = (a.h + seg - 1) / seg;
+    int segs = (a.h + seg - 1) / seg;
+    seg = (((a.h + segs - 1) / segs) + 7) & ~7;     // even segments (1080 rows: 5 x 216 instead of 4 x 256 + 56)
+    segs = (a.h + seg - 1) / seg;
     const long long items = (long long) strips * segs * n_frames;
     if (items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int grid = (int) (items < 2LL * sm_count ? items : 2LL * sm_count);
