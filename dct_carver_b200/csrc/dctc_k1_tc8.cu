@@ -724,7 +724,8 @@ cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, 
     const int strips = (a.w + MW - 1) / MW;
     // segment height: long segments amortise the 8-row prologue; keep >= ~6 items per SM so the tail stays short
     int seg = 256;   // (measured on 16 frames of 4K: 1024/512 rows 50.5 us per frame, 256 rows 49.3, 128 rows 50.5, 64 rows 54.7)
-    while (seg > 32 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 12LL * sm_count) seg >>= 1;
+    // (one 4K frame per launch: 70.9 us with >= 6 items per SM, 80.8 us with >= 8 or 12, 74.7 us with >= 2)
+    while (seg > 32 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 6LL * sm_count) seg >>= 1;
     int segs = (a.h + seg - 1) / seg;
     seg = (((a.h + segs - 1) / segs) + 7) & ~7;     // even segments (1080 rows: 5 x 216 instead of 4 x 256 + 56)
     segs = (a.h + seg - 1) / seg;
