@@ -145,15 +145,17 @@ __device__ __forceinline__ void dp_st_cluster_s32(uint32_t ra, int v) { asm vola
 // the current batch is walked, and its cp.async copies land while the walk (a chain of dependent shared-memory reads)
 // is running.
 constexpr int DP_WIN = 144;       // back-track window (floats); the cumulative plane's pitch is at least this
+constexpr int DP_WINP = DP_WIN + 4;   // window row in shared memory: 3 pad floats, the left sentinel, DP_WIN columns
 
 __device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, size_t m_pitch, int w, int h, int x,
                                              int* __restrict__ seam, int* __restrict__ seam_log,
-                                             float (*win)[32][DP_WIN], int lane)
+                                             float (*win)[32][DP_WINP], int lane)
 {
     const float INF = __int_as_float(0x7f800000);
     if (lane == 0) { seam[h - 1] = x; if (seam_log) seam_log[h - 1] = x; }
     const int max_base = (int) m_pitch - DP_WIN;
-    // window rows of the batch that starts below image row ytop: window row i = image row ytop-1-i
+    // window rows of the batch that starts below image row ytop: window row i = image row ytop-1-i, column c of the
+    // plane at win[buf][i][4 + c - base]
     auto stage = [&](int ytop, int xs, int buf) -> int {
         int base = (xs - 66) & ~3;
         base = base < 0 ? 0 : (base > max_base ? max_base : base);
@@ -163,7 +165,7 @@ __device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, s
                 const int yy = ytop - 1 - i;
                 if (yy >= 0) {
                     const float* src = mplane + (size_t) yy * m_pitch + base + 4 * c;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(&win[buf][i][4 * c])), "l"(src) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(&win[buf][i][4 + 4 * c])), "l"(src) : "memory");
                 }
             }
         }
@@ -176,26 +178,28 @@ __device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, s
         const int base_next = stage(ytop - 32, x, buf ^ 1);     // lands while this batch is walked
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
+        // +inf sentinels left of column 0 and at column w (range clipping), so that the walk needs no bounds checks
+        if (base == 0) win[buf][lane][3] = INF;
+        if (w - base >= 0 && w - base < DP_WIN) win[buf][lane][4 + w - base] = INF;
+        __syncwarp();
         const int steps = ytop < 32 ? ytop : 32;
-        // the walk: three shared-memory reads and two compares per row; lane i remembers the column of step i and the
-        // 32 columns are written with one coalesced store at the end of the batch
+        // the walk: three shared-memory reads at immediate offsets, two compares, a few selects per row; lane i remembers
+        // the column of step i and the 32 columns are written with one coalesced store at the end of the batch
         int mine = 0;
-        const float* wb = &win[buf][0][0] - base;          // window row i, column x: wb[i * DP_WIN + x]
+        const float* wp = &win[buf][0][4] + (x - base);        // wp[0] = cumulative value at (window row, column x)
         auto walk = [&](int i) {
-            const float* wr = wb + i * DP_WIN + x;
-            const float a = x > 0 ? wr[-1] : INF;
-            const float b = wr[0];
-            const float c = x < w - 1 ? wr[1] : INF;
-            int arg = x - 1;
-            float best = a;
-            if (b < best) { best = b; arg = x; }
-            if (c < best) arg = x + 1;
-            x = arg;
+            const float a = wp[-1], b = wp[0], c = wp[1];
+            const bool p1 = b < a;
+            const float best = p1 ? b : a;
+            const bool p2 = c < best;
+            const int d = p2 ? 1 : (p1 ? 0 : -1);
+            x += d;
+            wp += DP_WINP + d;
             if (lane == i) mine = x;
         };
         if (steps == 32) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) walk(i);          // fully unrolled: row offsets become immediates
+            for (int i = 0; i < 32; i++) walk(i);
         } else {
             for (int i = 0; i < steps; i++) walk(i);
         }
@@ -266,7 +270,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     __shared__ __align__(8) unsigned long long ebar[DP_MAXW][DP_NST_MAX];
     __shared__ float red_v[DP_CL * DP_MAXW];      // per-strip minima, gathered in CTA 0 through distributed shared memory
     __shared__ int red_i[DP_CL * DP_MAXW];
-    __shared__ __align__(16) float win[2][32][DP_WIN];
+    __shared__ __align__(16) float win[2][32][DP_WINP];
     const int tid = threadIdx.x, lane = tid & 31;
     const int wpc = blockDim.x >> 5;                        // warps (strips) per CTA
     const uint32_t rank = dp_cta_rank();
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(32) dctc_seam_incr_kernel(const float* __restr
     int* xsb = reinterpret_cast<int*>(buf + 2 * (INCR_CAP + 4));           // first staged column per slot
     int* bmin = xsb + INCR_D;                                              // band of the removed seam per row
     int* bmax = bmin + h;
-    __shared__ __align__(16) float win[2][32][DP_WIN];
+    __shared__ __align__(16) float win[2][32][DP_WINP];
     const int lane = threadIdx.x;
     const float INF = __int_as_float(0x7f800000);
     if (lane == 0) *rebuild_flag = 0;

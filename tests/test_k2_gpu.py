@@ -193,6 +193,29 @@ def test_device_seam_loop_incremental_map_equals_rebuild(ctx, b, ch, w, h, n, pa
     assert 0 <= rebuilds < n
 
 
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_device_seam_loop_hugs_the_image_border(ctx, side):
+    """Only the outermost column has zero energy (its edge-replicated window is flat), so every seam runs down the
+    image border: exercises the range clipping of the seam DP and of the back-track windows (+inf sentinels left of
+    column 0 and at column w) against the host carver."""
+    from dct_carver_b200 import host
+    w, h, n = 203, 77, 4
+    img = ol.synth_image(w, h, 3, 909, 0)
+    if side == "right":
+        img[:, -4:, :] = 128
+    else:
+        img[:, :5, :] = 128
+    ctx.set_params(8, 0.5, 0.5)
+    want = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, device_loop=False)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.carver_load(img)
+    seams = ctx.carver_resize_width(n)
+    assert np.array_equal(seams, want["seams"])
+    edge = seams[0]
+    assert (edge == (w - 1 if side == "right" else 0)).all(), edge
+    assert np.array_equal(ctx.carver_image().reshape(want["image"].shape), want["image"])
+
+
 def test_device_seam_loop_ties_and_flat_image(ctx):
     """Constant image: every energy is 0, every cumulative value ties; liblqr's rule then removes column 0 in every
     row, every time (leftmost minimum, first strict minimum among parents)."""
