@@ -122,10 +122,14 @@ int dctc_set_params(dctc_context* ctx, const DctcEnergyParameters* p)
     if (!ctx || !p) return DCTC_ERR_INVALID;
     if (!valid_blocksize(p->blocksize)) return DCTC_ERR_BLOCKSIZE;
     if (!(std::isfinite(p->edges) && std::isfinite(p->textures))) return DCTC_ERR_INVALID;
+    const bool changed = ctx->edges != p->edges || ctx->textures != p->textures || ctx->blocksize != p->blocksize;
     ctx->edges = p->edges;
     ctx->textures = p->textures;
     ctx->blocksize = p->blocksize;
     ctx->mirror_valid = false;
+    // a loaded carver session keeps its map in step with the operator (band radius, weights), like liblqr, whose
+    // lqr_carver_set_energy_function (src/render.c:314-315) invalidates the energy map
+    if (changed && ctx->c_img) return dctc_carver_params_changed(ctx);
     return DCTC_OK;
 }
 

@@ -145,7 +145,8 @@ __device__ __forceinline__ void dp_st_cluster_s32(uint32_t ra, int v) { asm vola
 // the current batch is walked, and its cp.async copies land while the walk (a chain of dependent shared-memory reads)
 // is running.
 constexpr int DP_WIN = 144;       // back-track window (floats); the cumulative plane's pitch is at least this
-constexpr int DP_WINP = DP_WIN + 4;   // window row in shared memory: 3 pad floats, the left sentinel, DP_WIN columns
+constexpr int DP_WINP = DP_WIN + 8;   // window row in shared memory: 3 pad floats, the left sentinel, DP_WIN columns, the right
+                                      // sentinel (needed when the window ends exactly at column w) and 3 pad floats
 
 __device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, size_t m_pitch, int w, int h, int x,
                                              int* __restrict__ seam, int* __restrict__ seam_log,
@@ -180,7 +181,7 @@ __device__ __forceinline__ void dp_backtrack(const float* __restrict__ mplane, s
         __syncwarp();
         // +inf sentinels left of column 0 and at column w (range clipping), so that the walk needs no bounds checks
         if (base == 0) win[buf][lane][3] = INF;
-        if (w - base >= 0 && w - base < DP_WIN) win[buf][lane][4 + w - base] = INF;
+        if (w - base >= 0 && w - base <= DP_WIN) win[buf][lane][4 + w - base] = INF;   // <=: w == base + DP_WIN lands in the row's tail pad
         __syncwarp();
         const int steps = ytop < 32 ? ytop : 32;
         // the walk: three shared-memory reads at immediate offsets, two compares, a few selects per row; lane i remembers
@@ -826,17 +827,36 @@ static void carver_args(const dctc_context* ctx, DctcK1Args& a)
 
 static int band_stride(const dctc_context* ctx) { return 4 * (ctx->blocksize / 2); }
 
-extern "C" {
-
-int dctc_carver_load(dctc_context* ctx, const uint8_t* img, int w, int h, int channels, size_t pitch)
+// Full energy map of the session's current image.  A carver session keeps one arithmetic for the whole seam loop: the
+// per-seam band updates run in the FP32 tile kernel, so full maps use the bit-identical FP32 march kernel rather than
+// the tensor-core kernel (liblqr: update_emap must reproduce what build_emap would give on the carved image).
+static int carver_full_energy(dctc_context* ctx)
 {
-    if (!ctx || !img || w <= 0 || h <= 0 || channels < 1 || channels > 4 || pitch < (size_t) w * channels)
-        return DCTC_ERR_INVALID;
-    const int b = ctx->blocksize;
-    if (!(b == 2 || b == 4 || b == 8 || b == 16)) return DCTC_ERR_BLOCKSIZE;
+    DctcK1Args a;
+    carver_args(ctx, a);
+    const int saved_kernel = ctx->kernel;
+    if (ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_TC_SPLIT) ctx->kernel = DCTC_KERNEL_FP32_MARCH;
+    const int rc = dctc_run_k1(ctx, a, 1, ctx->stream);
+    ctx->kernel = saved_kernel;
+    return rc;
+}
+
+// dctc_set_params with a session loaded (liblqr: lqr_carver_set_energy_function invalidates the energy map): the
+// resident map is rebuilt with the new operator and the cumulative plane of the seam DP is dropped.
+int dctc_carver_params_changed(dctc_context* ctx)
+{
+    if (!ctx->c_img) return DCTC_OK;
     CK(ctx, cudaSetDevice(ctx->device));
+    ctx->mirror_valid = false;
+    ctx->c_m_valid = false;
+    const int rc = carver_full_energy(ctx);
+    if (rc) return rc;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    dctc_carver_release(ctx);
+    return DCTC_OK;
+}
+
+static int carver_load_impl(dctc_context* ctx, const uint8_t* img, int w, int h, int channels, size_t pitch)
+{
     ctx->c_w0 = ctx->c_w = w; ctx->c_h = h; ctx->c_ch = channels;
     ctx->c_pitch = ((size_t) w * channels + 15) & ~(size_t) 15;
     const size_t npx = (size_t) w * h;
@@ -850,18 +870,27 @@ int dctc_carver_load(dctc_context* ctx, const uint8_t* img, int w, int h, int ch
     CK(ctx, cudaMallocHost((void**) &ctx->h_band, sizeof(float) * (size_t) h * 32 + sizeof(int) * h));
     CK(ctx, cudaMemcpy2DAsync(ctx->c_img, ctx->c_pitch, img, pitch, (size_t) w * channels, h, cudaMemcpyHostToDevice,
                               ctx->stream));
-    DctcK1Args a;
-    carver_args(ctx, a);
-    // A carver session keeps one arithmetic for the whole seam loop: the per-seam band updates run in the FP32 tile
-    // kernel, so the initial full map uses the bit-identical FP32 march kernel rather than the tensor-core kernel
-    // (liblqr: update_emap must reproduce what build_emap would give on the carved image).
-    const int saved_kernel = ctx->kernel;
-    if (ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_TC_SPLIT) ctx->kernel = DCTC_KERNEL_FP32_MARCH;
-    int rc = dctc_run_k1(ctx, a, 1, ctx->stream);
-    ctx->kernel = saved_kernel;
+    int rc = carver_full_energy(ctx);
     if (rc) return rc;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return DCTC_OK;
+}
+
+extern "C" {
+
+int dctc_carver_load(dctc_context* ctx, const uint8_t* img, int w, int h, int channels, size_t pitch)
+{
+    if (!ctx || !img || w <= 0 || h <= 0 || channels < 1 || channels > 4 || pitch < (size_t) w * channels)
+        return DCTC_ERR_INVALID;
+    const int b = ctx->blocksize;
+    if (!(b == 2 || b == 4 || b == 8 || b == 16)) return DCTC_ERR_BLOCKSIZE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    dctc_carver_release(ctx);
+    // a half-built session (an allocation or the upload failed) must not look loaded to the next call
+    const int rc = carver_load_impl(ctx, img, w, h, channels, pitch);
+    if (rc) dctc_carver_release(ctx);
+    return rc;
 }
 
 int dctc_carver_width(const dctc_context* ctx) { return ctx ? ctx->c_w : 0; }
@@ -897,6 +926,8 @@ int dctc_carve_and_update(dctc_context* ctx, const int* seam_x, float* band_out,
     int* h_seam = (int*) ((char*) ctx->h_band + sizeof(float) * (size_t) h * 32);
     for (int y = 0; y < h; y++) {
         if (seam_x[y] < 0 || seam_x[y] >= w_old) return DCTC_ERR_STATE;
+        // connected seams only (delta_x = 1, src/render.c:313): the band width 4*(b/2) and the band tiles rely on it
+        if (y > 0 && (seam_x[y] - seam_x[y - 1] > 1 || seam_x[y - 1] - seam_x[y] > 1)) return DCTC_ERR_INVALID;
         h_seam[y] = seam_x[y];
     }
     CK(ctx, cudaSetDevice(ctx->device));

@@ -2,8 +2,10 @@
 //
 // The plug-in's "output energy" option (src/render.c:175-202) asks liblqr for an 8-bit grey rendering of the energy
 // map: lqr_carver_get_energy_image(carver, buf, orientation, LQR_COLDEPTH_8I, LQR_GREY_IMAGE) at src/render.c:191.
-// liblqr compresses e -> e/(1+e), min-max normalises to [0,1] and quantises [liblqr, from memory; restated in
-// dct_carver_b200/host/dctc_lqr.c:dctc_lqr_carver_get_energy_image].  Two HBM-bound passes over the float plane:
+// liblqr compresses e -> 1/(1 + 1/e) (= e/(1+e); 0 for e = 0), min-max normalises to [0,1] in float and quantises by
+// truncation, (guchar)(val * 255) as lqr_pixel_set_norm does for LQR_COLDEPTH_8I [liblqr 0.4.x lqr_energy.c /
+// lqr_carver_rw.c, from memory: PARITY UNPINNED; restated in dct_carver_b200/host/dctc_lqr.c:
+// dctc_lqr_carver_get_energy_image].  Two HBM-bound passes over the float plane:
 // a min/max reduction of the compressed values (4 B/px read) and the scale + quantise pass (4 B/px read, 1 B/px
 // written).  The FP32 operation order is the host's, so the bytes are identical.  When the map is sharded into row
 // bands the (lo, hi) pair is what the ranks all-reduce (min, max) between the two passes.
@@ -19,6 +21,9 @@
 
 namespace {
 
+// e >= 0 -> 1 / (1 + 1/e), IEEE divisions (1/0 = inf, 1/inf = 0): the same two roundings as the host carver
+__device__ __forceinline__ float dctc_k3_compress(float e) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, __fdiv_rn(1.0f, e))); }
+
 // compressed values are >= 0, so their bit patterns order like unsigned integers
 __global__ void __launch_bounds__(256) dctc_minmax_kernel(const float* __restrict__ en, size_t pitch, int w, int h,
                                                           unsigned int* __restrict__ lo_hi)
@@ -27,8 +32,7 @@ __global__ void __launch_bounds__(256) dctc_minmax_kernel(const float* __restric
     for (int y = blockIdx.y; y < h; y += gridDim.y) {
         const float* row = en + (size_t) y * pitch;
         for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
-            const float e = row[x];
-            const float c = e / (1.0f + e);
+            const float c = dctc_k3_compress(row[x]);
             lo = fminf(lo, c);
             hi = fmaxf(hi, c);
         }
@@ -66,11 +70,9 @@ __global__ void __launch_bounds__(256) dctc_energy_image_kernel(const float* __r
         const float* row = en + (size_t) y * pitch;
         uint8_t* orow = out + (size_t) y * out_pitch;
         for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
-            const float e = row[x];
-            const float c = e / (1.0f + e);
-            // same FP32 operation order as the host carver: 255 * (c - lo), then / span, then + 0.5, truncate
-            const float t = __fmul_rn(255.0f, __fsub_rn(c, lo));
-            orow[x] = hi > lo ? (uint8_t) __fadd_rn(__fdiv_rn(t, span), 0.5f) : (uint8_t) 0;
+            const float c = dctc_k3_compress(row[x]);
+            // same FP32 operation order as the host carver: (c - lo) / span, then * 255, truncate
+            orow[x] = hi > lo ? (uint8_t) __fmul_rn(__fdiv_rn(__fsub_rn(c, lo), span), 255.0f) : (uint8_t) 0;
         }
     }
 }

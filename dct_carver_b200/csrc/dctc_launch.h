@@ -69,3 +69,4 @@ struct dctc_context {
 
 int dctc_fail_cuda(dctc_context* ctx, cudaError_t e);
 void dctc_carver_release(dctc_context* ctx);
+int dctc_carver_params_changed(dctc_context* ctx);   // rebuilds the resident energy map of a loaded carver session

@@ -453,10 +453,10 @@ int dctc_lqr_carver_get_energy_image(DctcLqrCarver *r, uint8_t *buffer)
     if (!e) return DCTC_LQR_NOMEM;
     rc = dctc_lqr_carver_get_energy(r, e);
     if (rc) { free(e); return rc; }
-    for (i = 0; i < n; i++) e[i] = e[i] / (1.0f + e[i]);
+    for (i = 0; i < n; i++) e[i] = 1.0f / (1.0f + (1.0f / e[i]));   /* liblqr's soft compression; e = 0 -> 0 */
     lo = hi = e[0];
     for (i = 1; i < n; i++) { if (e[i] < lo) lo = e[i]; if (e[i] > hi) hi = e[i]; }
-    for (i = 0; i < n; i++) buffer[i] = hi > lo ? (uint8_t) (255.0f * (e[i] - lo) / (hi - lo) + 0.5f) : 0;
+    for (i = 0; i < n; i++) buffer[i] = hi > lo ? (uint8_t) (((e[i] - lo) / (hi - lo)) * 255.0f) : 0;   /* lqr_pixel_set_norm truncates */
     free(e);
     return DCTC_LQR_OK;
 }

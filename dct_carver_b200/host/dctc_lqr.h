@@ -60,7 +60,7 @@ int dctc_lqr_carver_scan_line(DctcLqrCarver *r, int *n, uint8_t **rgb);
 /* current energy map (w*h floats, building it if needed) — lqr_carver_get_energy */
 int dctc_lqr_carver_get_energy(DctcLqrCarver *r, float *buffer);
 /* 8-bit grey energy image as lqr_carver_get_energy_image(.., LQR_COLDEPTH_8I, LQR_GREY_IMAGE) (src/render.c:191):
- * e -> e/(1+e), min-max normalised to 0..255 */
+ * e -> 1/(1+1/e), min-max normalised, (uint8_t)(val*255) [liblqr, from memory] */
 int dctc_lqr_carver_get_energy_image(DctcLqrCarver *r, uint8_t *buffer);
 /* visibility map over the ORIGINAL w0*h0 frame: 0 = never carved, k = removed by the k-th seam (src/render.c:214-231) */
 const int *dctc_lqr_carver_vmap(const DctcLqrCarver *r, int *w0, int *h0, int *depth);

@@ -72,7 +72,9 @@ enum {
 int dctc_create(dctc_context **ctx, int device);
 /* Frees device buffers, pinned staging and the stream.  Counterpart of the frees at src/render.c:413-416. */
 void dctc_destroy(dctc_context *ctx);
-/* edges / textures / blocksize as PlugInVals carries them (src/main.h:12-22, src/main.c:151-153). */
+/* edges / textures / blocksize as PlugInVals carries them (src/main.h:12-22, src/main.c:151-153).  With a carver
+ * session loaded, a change of any of the three rebuilds the session's resident energy map with the new operator
+ * (liblqr: lqr_carver_set_energy_function invalidates the map, src/render.c:314-315). */
 int dctc_set_params(dctc_context *ctx, const DctcEnergyParameters *params);
 int dctc_set_kernel(dctc_context *ctx, int kernel);
 int dctc_last_cuda_error(const dctc_context *ctx);
@@ -89,7 +91,10 @@ unsigned long long dctc_launch_count(const dctc_context *ctx);
  * Replaces liblqr's build_emap loop "for y<h for x<w: en = dct_pixel_energy(x,y,w,h,rw,extra)"
  * (callback src/render.c:134-157; dctNxN src/dct.c:77-94; weighted_max_dct_correlation src/dct.c:96-110)
  * over the interleaved 8-bit buffer that lqr_carver_new() receives (src/render.c:310-312), with the
- * LQR_ER_LUMA reader fused in.  out[y*w+x] is the gfloat the callback would return. */
+ * LQR_ER_LUMA reader fused in.  out[y*w+x] is the gfloat the callback would return.
+ * Device-pointer variants: every row must be readable for its full pitch_bytes (the kernels stage rows in 16-byte
+ * chunks up to the pitch), i.e. the buffer spans h*pitch_bytes; the host-buffer variants copy exactly w*channels
+ * bytes per row into their own 16-byte-pitched staging. */
 int dctc_energy_full(dctc_context *ctx, const uint8_t *img, int w, int h, int channels, size_t pitch_bytes,
                      float *out);
 
@@ -133,7 +138,9 @@ int dctc_carver_energy(dctc_context *ctx, float *out);
  * energy planes and recomputes the energy only in the band the seam touched:
  *   row y: x in [min_{|y'-y|<=r} seam_x[y'] - r, max_{|y'-y|<=r} seam_x[y'] + r - 1] clipped to [0, w-2].
  * On return *xmin / *xmax (h entries each, may be NULL) hold that band and band_out (may be NULL) receives, row
- * by row, the xmax[y]-xmin[y]+1 recomputed values packed back to back. */
+ * by row, the xmax[y]-xmin[y]+1 recomputed values packed back to back (at most 4*(blocksize/2) per row: band_out needs
+ * room for h*4*(blocksize/2) floats).  The seam must be connected, |seam_x[y]-seam_x[y-1]| <= 1, as liblqr's are with
+ * delta_x = 1 (src/render.c:313); anything else returns DCTC_ERR_INVALID, a column outside [0, w) DCTC_ERR_STATE. */
 int dctc_carve_and_update(dctc_context *ctx, const int *seam_x, float *band_out, int *xmin, int *xmax);
 /* Copies the current (carved) interleaved image back to the host, pitch = w*channels. */
 int dctc_carver_image(dctc_context *ctx, uint8_t *out);
@@ -162,8 +169,8 @@ int dctc_carver_paint_seams(dctc_context *ctx, uint8_t *img, int channels, size_
 
 /* ---- K3: energy-image export ------------------------------------------------------------------------------
  * Replaces lqr_carver_get_energy_image(carver, buf, orientation, LQR_COLDEPTH_8I, LQR_GREY_IMAGE) as called at
- * src/render.c:191 (the plug-in's "output energy" option, src/render.c:175-202): e -> e/(1+e), min-max normalise,
- * 8-bit grey. */
+ * src/render.c:191 (the plug-in's "output energy" option, src/render.c:175-202): e -> 1/(1+1/e) (= e/(1+e)),
+ * min-max normalise in float, 8-bit grey by truncation (guchar)(val*255) [liblqr, from memory: parity unpinned]. */
 
 /* (min, max) of e/(1+e) over a device-resident w*h float plane; lo_hi receives two floats.  For a map sharded into
  * row bands each rank calls this on its band and the pairs are all-reduced (min, max) before dctc_energy_image_dev. */

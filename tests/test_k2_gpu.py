@@ -138,9 +138,10 @@ def test_gpu_retarget_height_and_energy_image(ctx):
     got = host.render(img, -6, 8, vertically=True, ctx=ctx, output_energy=True)
     assert got["image"].shape == (64, 64, 3)
     en = ctx.energy_full(img).astype(np.float32)
-    e = en / (1.0 + en)
-    want = np.floor(255.0 * (e - e.min()) / (e.max() - e.min()) + 0.5).astype(np.uint8)
-    assert np.abs(got["energy_image"].astype(int) - want.astype(int)).max() <= 1
+    with np.errstate(divide="ignore"):
+        e = (np.float32(1) / (np.float32(1) + np.float32(1) / en)).astype(np.float32)
+    want = (((e - e.min()) / (e.max() - e.min())) * np.float32(255)).astype(np.uint8)     # truncation, FP32 throughout
+    assert np.array_equal(got["energy_image"], want)
 
 
 @pytest.mark.parametrize("b,ch,w,h,n", [(8, 3, 150, 90, 25), (8, 1, 97, 75, 40), (4, 3, 64, 33, 10), (16, 3, 130, 70, 12),
@@ -239,16 +240,18 @@ def test_device_seam_loop_state_errors(ctx):
 
 @pytest.mark.parametrize("ch,w,h", [(3, 130, 77), (1, 64, 33), (3, 1, 1)])
 def test_energy_image_export_equals_host_formula(ctx, ch, w, h):
-    """K3 (lqr_carver_get_energy_image semantics, src/render.c:191): e/(1+e), min-max, 8-bit — byte-identical to the
-    host formula evaluated in FP32 on the same energies, also when (lo, hi) are supplied from outside (band sharding)."""
+    """K3 (lqr_carver_get_energy_image semantics, src/render.c:191): 1/(1+1/e), min-max, 8-bit by truncation
+    [liblqr, from memory: parity unpinned] — byte-identical to the host formula evaluated in FP32 on the same energies,
+    also when (lo, hi) are supplied from outside (band sharding)."""
     img = ol.synth_image(w, h, ch, 31, 3)
     ctx.set_params(8, 0.5, 0.5)
     ctx.carver_load(img)
     en = ctx.carver_energy()
-    c = en / (np.float32(1.0) + en)
+    with np.errstate(divide="ignore"):
+        c = (np.float32(1.0) / (np.float32(1.0) + np.float32(1.0) / en)).astype(np.float32)
     lo, hi = c.min(), c.max()
     if hi > lo:
-        want = ((np.float32(255.0) * (c - lo)) / (hi - lo) + np.float32(0.5)).astype(np.uint8)
+        want = (((c - lo) / (hi - lo)) * np.float32(255.0)).astype(np.uint8)
     else:
         want = np.zeros((h, w), np.uint8)
     got = ctx.carver_energy_image()
