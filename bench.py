@@ -3,13 +3,16 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 4k|batch1080p|gigapixel]
 
-A "step" is one pass of the hot path over one batch of synthetic frames that is larger than L2:
+A "step" is one pass of the hot path over one batch of synthetic frames that is far larger than L2:
   4k          (default; BASELINE configs[1]) F distinct 3840x2160 RGB frames per GPU, one batched K1 launch
   batch1080p  (configs[3]) F distinct 1920x1080 RGB frames per GPU, frames sharded over ranks, no collective
   gigapixel   (configs[4]) one 32768x32768 RGB image split into row bands over the ranks; the halo rows are read
               straight from the neighbour rank's HBM over NVLink (CUDA IPC peer pointers) inside the K1 kernel
-One process per GPU; for N>1 launch through torch.distributed.run (NCCL is used only for the barrier and the
-max-over-ranks of the device time).  Rank 0 prints ONE JSON line.
+One process per GPU; for N>1 launch through torch.distributed.run (torch.distributed/NCCL is used only for the barrier
+and the max-over-ranks of the device time; the data path, including the band plumbing, is the C library).
+Rank 0 prints ONE JSON line.  Besides the headline it carries `configs`: every BASELINE config and the block-size sweep
+measured in the same run (C1 512x512 grey, C2 one frame per launch, C3 480-seam retarget, C4 1080p batch, C5 gigapixel),
+each with its own roofline fraction.
 """
 import argparse
 import ctypes as C
@@ -31,9 +34,10 @@ UNIT = "Mpix/s"
 BYTES_PER_PX = {3: 7.0, 1: 5.0, 4: 8.0, 2: 6.0}   # u8 channels in + float32 energy out
 SEED = 0xD0C7CA13
 
+# frames per GPU per step are sized so that the driver's 20 timed steps keep the device busy for ~0.5 s
 WORKLOADS = {
-    "4k": dict(w=3840, h=2160, ch=3, frames=16, desc="3840x2160 RGB full energy map, blocksize 8, edges=textures=0.5"),
-    "batch1080p": dict(w=1920, h=1080, ch=3, frames=64, desc="batch of 1920x1080 RGB frames, full energy maps"),
+    "4k": dict(w=3840, h=2160, ch=3, frames=512, desc="3840x2160 RGB full energy map, blocksize 8, edges=textures=0.5"),
+    "batch1080p": dict(w=1920, h=1080, ch=3, frames=2048, desc="batch of 1920x1080 RGB frames, full energy maps"),
     "gigapixel": dict(w=32768, h=32768, ch=3, frames=1, desc="32768x32768 RGB, row bands + NVLink peer halo reads"),
 }
 
@@ -64,6 +68,14 @@ def kernel_note(blocksize):
     return base + "blocksize 16 runs in the FP32 tile kernel (FP32-pipe bound)"
 
 
+def shared_config(args, wl):
+    """Identical in the `ours` and `reference` arms (the driver compares the two records)."""
+    return {"workload": wl["desc"].replace("blocksize 8", "blocksize %d" % args.blocksize), "blocksize": args.blocksize,
+            "edges": 0.5, "textures": 0.5, "frames_per_gpu_per_step": wl["frames"],
+            "l2": "inputs+outputs per step exceed L2 (distinct frames)",
+            "parallelism": "frames sharded, no collective" if args.workload != "gigapixel" else "row bands"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -75,12 +87,13 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock, power and throttle reasons through NVML while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
+        self.power = []
         self.reasons = set()
         self.max_mhz = None
         self._halt = threading.Event()
@@ -110,6 +123,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -125,15 +142,16 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+        return {"sm_mhz": statistics.median(self.samples), "sm_min_mhz": min(self.samples), "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(self.power) if self.power else None,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_rate(wl, seconds_target=12.0, frame=0):
+def cpu_reference_rate(wl, seconds_target=12.0, frame=0, blocksize=8, threads=None):
     """Times the reference's own CPU path (oracle/_ref when it was compiled, else the oracle port) on a bounded
     sample of the workload: a block of full-width rows of one synthetic frame, all host threads."""
     import oracle_lib as ol
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     kind = "reference" if ol.ref() is not None else "port"
     w, ch = wl["w"], wl["ch"]
     fn = ol.ref_energy if kind == "reference" else ol.oracle_energy
@@ -142,7 +160,7 @@ def cpu_reference_rate(wl, seconds_target=12.0, frame=0):
         hh = rows + 16
         img = ol.synth_image(w, hh, ch, SEED, 0, frame=frame, y_offset=1000)
         t0 = time.perf_counter()
-        fn(img, 8, 0.5, 0.5, nthreads=cores)
+        fn(img, blocksize, 0.5, 0.5, nthreads=cores)
         return (time.perf_counter() - t0), w * hh
 
     t, px = run(max(cores, 16))
@@ -162,7 +180,7 @@ def run_reference(args, rank, world):
     total_t = 0.0
     target = max(1.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
     for s in range(args.warmup + args.steps):
-        cb, t, px = cpu_reference_rate(wl, seconds_target=target, frame=s)
+        cb, t, px = cpu_reference_rate(wl, seconds_target=target, frame=s, blocksize=args.blocksize)
         if s >= args.warmup:
             vals.append(px / t / 1e6)
             total_t += t
@@ -171,9 +189,9 @@ def run_reference(args, rank, world):
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, len(vals)), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "blocksize": 8, "edges": 0.5, "textures": 0.5,
-                   "note": "reference CPU path (src/dct.c + fft2d via the LqrEnergyFunc callback), host threads only"},
+        "scaling": "strong" if args.workload == "gigapixel" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": shared_config(args, wl),
+        "impl_note": "reference CPU path (src/dct.c + fft2d via the LqrEnergyFunc callback), host threads only; each step is the bounded sample in cpu_baseline.sample",
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,10 +199,126 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ---- per-config measurements (the `configs` sub-record) ---------------------------------------------------------
+
+class Timer:
+    """CUDA-event timing on the context stream; for N>1 the max over ranks."""
+
+    def __init__(self, ctx, dist, torch):
+        self.ctx, self.dist, self.torch = ctx, dist, torch
+
+    def barrier(self):
+        self.ctx.sync()
+        if self.dist is not None:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+
+    def ms(self, fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        fn()
+        self.ctx.timer_begin()
+        for _ in range(reps):
+            fn()
+        ms = self.ctx.timer_end()
+        self.barrier()
+        if self.dist is not None:
+            t = self.torch.tensor([ms], device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / reps
+
+
+def roof(px_per_launch, ch, ms, hbm_peak):
+    gbs = BYTES_PER_PX[ch] * px_per_launch / (ms * 1e-3) / 1e9
+    return {"ms_per_launch": ms, "Mpix_s": px_per_launch / (ms * 1e-3) / 1e6, "achieved_GBs": gbs, "roofline_frac": gbs / hbm_peak}
+
+
+def frames_config(ctx, timer, w, h, ch, frames, per_launch, reps, hbm_peak, seed, first_frame=0, d_in=None, d_out=None):
+    """`frames` distinct device-resident frames; every launch processes `per_launch` of them, rotating through the pool."""
+    pitch = w * ch
+    fs = pitch * h
+    own = d_in is None
+    if own:
+        d_in = ctx.dev_alloc(frames * fs)
+        d_out = ctx.dev_alloc(frames * w * h * 4)
+        ctx.synth_fill_dev(d_in, frames, fs, w, h, ch, pitch, seed, 0, first_frame=first_frame)
+        ctx.sync()
+    per_launch = min(per_launch, frames)
+    state = {"i": 0}
+    groups = max(1, frames // per_launch)
+
+    def step():
+        g = state["i"] % groups
+        state["i"] += 1
+        ctx.energy_batch_dev(d_in + g * per_launch * fs, per_launch, fs, w, h, ch, pitch, d_out + g * per_launch * w * h * 4, w * h, w)
+    ms = timer.ms(step, reps)
+    if own:
+        ctx.dev_free(d_in)
+        ctx.dev_free(d_out)
+    r = roof(per_launch * w * h, ch, ms, hbm_peak)
+    r.update({"frames_per_launch": per_launch, "distinct_frames": frames, "launches_timed": reps})
+    return r
+
+
+def config_c3(ctx_args, hbm_peak):
+    """BASELINE config 3: 1920x1080 RGB -> 1440x1080 (480 vertical seams), whole loop on the device, and the same through
+    the host carver as the cross-check of the seams."""
+    import dct_carver_b200 as dc
+    from dct_carver_b200 import host
+    import oracle_lib as ol   # synthetic image generator only
+    w, h, n = 1920, 1080, 480
+    img = ol.synth_image(w, h, 3, SEED + 2, 0)
+    ctx = dc.Context(ctx_args["device"], blocksize=8, edges=0.5, textures=0.5)
+    ctx.carver_load(img[:256, :256])
+    ctx.carver_resize_width(8)          # warm-up (module load, first launches)
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    ctx.carver_load(img)
+    t_load = time.perf_counter() - t0
+    ctx.timer_begin()
+    seams = ctx.carver_resize_width(n)
+    ms_loop = ctx.timer_end()
+    launches = ctx.launches - l0
+    t1 = time.perf_counter()
+    r2 = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, device_loop=True)          # the drop-in call a reference user makes
+    t_render = time.perf_counter() - t1
+    t2 = time.perf_counter()
+    want = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, device_loop=False)       # host carver (liblqr stand-in) + GPU energy
+    t_host = time.perf_counter() - t2
+    same = bool(np.array_equal(seams, want["seams"])) and bool(np.array_equal(r2["seams"], want["seams"])) and \
+        bool(np.array_equal(r2["image"], want["image"]))
+    ctx.close()
+    band_px = n * h * 10   # ~ (2r + spread) x h pixels recomputed per seam (SURVEY section 8d)
+    return {"workload": "1920x1080 RGB -> 1440x1080, 480 vertical seams, blocksize 8, device-resident seam loop",
+            "us_per_seam": 1e3 * ms_loop / n, "seam_loop_s": ms_loop * 1e-3, "load_and_full_map_s": t_load,
+            "dctc_render_total_s": t_render, "host_carver_total_s": t_host, "gpu_launches": launches,
+            "seams_identical_to_host_carver": same,
+            "band_Mpix_s": band_px / (ms_loop * 1e-3) / 1e6,
+            "roofline_frac": 7.0 * band_px / (ms_loop * 1e-3) / 1e9 / hbm_peak,
+            "note": "latency-bound by design (one seam depends on the previous one): ~10 x 1080 px recomputed per seam"}
+
+
+def gigapixel_config(ctx, timer, rank, world, hbm_peak, reps, rendezvous, w=32768, h=32768, ch=3):
+    import dct_carver_b200 as dc
+    runner = dc.BandRunner(ctx, rendezvous, rank, world, w, h, ch)
+    runner.synth(SEED + 4)
+    runner.connect()
+    ms = timer.ms(lambda: runner.step(), reps, warm=2)
+    px = w * h
+    out = {"workload": "32768x32768 RGB, %d row band(s), halo rows read from the neighbour's HBM (C band runner)" % world,
+           "n_gpus": world, "ms_per_pass": ms, "Mpix_s": px / (ms * 1e-3) / 1e6,
+           "roofline_frac_per_gpu": BYTES_PER_PX[ch] * px / world / (ms * 1e-3) / 1e9 / hbm_peak,
+           "band_rows_per_gpu": runner.band_rows}
+    runner.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
@@ -193,12 +327,15 @@ def main():
     ap.add_argument("--blocksize", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config sub-record (C1..C5, block-size sweep)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.frames:
+        WORKLOADS[args.workload]["frames"] = args.frames
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -213,26 +350,24 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import dct_carver_b200 as dc
-    wl = dict(WORKLOADS[args.workload])
-    if args.frames:
-        wl["frames"] = args.frames
+    wl = WORKLOADS[args.workload]
     w, h, ch, F = wl["w"], wl["h"], wl["ch"], wl["frames"]
     ctx = dc.Context(local_rank, blocksize=args.blocksize, edges=0.5, textures=0.5, kernel=args.kernel)
     hbm_peak, peak_kind = peaks()
+    timer = Timer(ctx, dist, torch)
+    barrier = timer.barrier
+    rendezvous = "bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", str(os.getppid())))
 
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            torch.cuda.synchronize()
-            dist.barrier()
-
+    runner = None
+    d_in = d_out = None
     if args.workload == "gigapixel":
-        from dct_carver_b200 import multigpu
-        runner = multigpu.BandRunner(ctx, dist, rank, world, w, h, ch, SEED)
+        runner = dc.BandRunner(ctx, rendezvous + "_main", rank, world, w, h, ch)
+        runner.synth(SEED)
+        runner.connect()
         step = runner.step
         px_per_step_rank = runner.band_rows * w
-        launches_per_step = 1
-        cfg_extra = {"band_rows_per_gpu": runner.band_rows, "halo": "NVLink peer loads via CUDA IPC" if world > 1 else "none (single band)"}
+        cfg_extra = {"band_rows_per_gpu": runner.band_rows,
+                     "halo": "NVLink peer loads via CUDA IPC (C band runner)" if world > 1 else "none (single band)"}
     else:
         pitch = w * ch
         fstride = pitch * h
@@ -244,8 +379,7 @@ def main():
         def step():
             ctx.energy_batch_dev(d_in, F, fstride, w, h, ch, pitch, d_out, w * h, w)
         px_per_step_rank = F * w * h
-        launches_per_step = 1
-        cfg_extra = {"frames_per_gpu_per_step": F}
+        cfg_extra = {}
 
     for _ in range(args.warmup):
         step()
@@ -277,22 +411,26 @@ def main():
     alg_bytes = BYTES_PER_PX[ch] * px_per_step_rank
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     traffic = None
+    traffic_src = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            per_px = tj.get("%s_b%d_k%d" % (args.workload, args.blocksize, args.kernel), {}).get("dram_bytes_per_px")
+            ent = tj.get("%s_b%d_k%d" % (args.workload, args.blocksize, args.kernel), {})
+            per_px = ent.get("dram_bytes_per_px")
             traffic = per_px * px_per_step_rank if per_px else None
+            traffic_src = ent.get("source")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_kind": "of " + peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel": kernel_name(args.blocksize, args.kernel), "note": kernel_note(args.blocksize)}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_kind": "of " + peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": kernel_name(args.blocksize, args.kernel), "arithmetic": arithmetic(args.blocksize, args.kernel),
+                "note": kernel_note(args.blocksize)}
 
     # e2e: the same metric through the host-buffer C-ABI call, pinned host memory, copies inside the timed region
     e2e = None
     if not args.no_e2e and args.workload != "gigapixel":
-        Fe = min(F, 8)
+        Fe = min(F, 32)
         h_in = dc.pinned_array((Fe, h, w, ch), np.uint8)
         h_out = dc.pinned_array((Fe, h, w), np.float32)
         tmp = np.empty((h, w, ch), np.uint8)
@@ -302,7 +440,7 @@ def main():
         for _ in range(2):
             ctx.energy_batch(h_in, h_out)
         barrier()
-        ke = max(3, min(args.steps, 10))
+        ke = max(3, min(args.steps, 20))
         t0 = time.perf_counter()
         for _ in range(ke):
             ctx.energy_batch(h_in, h_out)
@@ -312,13 +450,77 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             te = float(t.item())
         e2e = {"value": Fe * w * h * world / te / 1e6, "unit": UNIT, "h2d_bytes_per_step": Fe * h * w * ch * world,
-               "d2h_bytes_per_step": Fe * h * w * 4 * world, "frames_per_step": Fe * world,
+               "d2h_bytes_per_step": Fe * h * w * 4 * world, "frames_per_step": Fe * world, "steps_timed": ke,
                "api": "dctc_energy_batch (host buffers, 3-slot H2D/compute/D2H overlap)"}
         assert float(np.abs(h_out[0]).max()) > 0.0
+        # the ceiling of that path: pinned-copy bandwidth with every rank copying at the same time
+        barrier()
+        pc = ctx.pcie_probe(256 << 20, 6)
+        barrier()
+        if dist is not None:
+            t = torch.tensor([pc["h2d_gbs"], pc["d2h_gbs"], pc["bidir_gbs_per_dir"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t)
+            pc = {"h2d_gbs": float(t[0]), "d2h_gbs": float(t[1]), "bidir_gbs_per_dir": float(t[2])}
+        bytes_in, bytes_out = float(w * h * ch), float(w * h * 4)
+        ceil = min(pc["bidir_gbs_per_dir"] * 1e9 / bytes_out, pc["bidir_gbs_per_dir"] * 1e9 / bytes_in) * w * h / 1e6
+        e2e["pcie"] = dict(pc, note="pinned cudaMemcpyAsync, 256 MiB x 6, all %d rank(s) copying concurrently; sum over ranks" % world)
+        e2e["pcie_ceiling_Mpix_s"] = ceil
+        e2e["frac_of_pcie_ceiling"] = e2e["value"] / ceil if ceil > 0 else None
+
+    # ---- every BASELINE config + the block-size sweep, in the same run -------------------------------------------
+    configs = None
+    if not args.no_configs and args.workload == "4k" and args.blocksize == 8:
+        configs = {}
+        if d_in is not None:
+            # C2 as ONE image per launch (the 512 resident frames are the rotation pool)
+            if world == 1:
+                configs["C2_one_frame_per_launch"] = frames_config(ctx, timer, w, h, ch, F, 1, 200, hbm_peak, SEED, d_in=d_in, d_out=d_out)
+                ctx.set_params(8, 0.8, 0.2)
+                configs["C2_weights_0.8_0.2"] = frames_config(ctx, timer, w, h, ch, F, 64, 5, hbm_peak, SEED, d_in=d_in, d_out=d_out)
+                ctx.set_params(8, 0.5, 0.5)
+                for b, per in ((2, 64), (4, 64), (16, 16)):
+                    ctx.set_params(b, 0.5, 0.5)
+                    r = frames_config(ctx, timer, w, h, ch, F, per, 5, hbm_peak, SEED, d_in=d_in, d_out=d_out)
+                    r["kernel"] = kernel_name(b, 0)
+                    configs["C2_blocksize_%d" % b] = r
+                ctx.set_params(8, 0.5, 0.5)
+            ctx.dev_free(d_in)
+            ctx.dev_free(d_out)
+            d_in = d_out = None
+        if world == 1:
+            c1 = frames_config(ctx, timer, 512, 512, 1, 512, 1, 400, hbm_peak, SEED + 1)
+            c1b = frames_config(ctx, timer, 512, 512, 1, 512, 512, 5, hbm_peak, SEED + 1)
+            configs["C1_512x512_grey"] = {"one_frame_per_launch": c1, "batch_of_512": c1b}
+            if not args.no_cpu_baseline:
+                try:
+                    cb1, _, _ = cpu_reference_rate(dict(w=512, h=512, ch=1), seconds_target=1.0, threads=1)
+                    configs["C1_512x512_grey"]["cpu_reference_1_thread_Mpix_s"] = cb1["value"]
+                except Exception as e:   # the checker is optional on the box
+                    configs["C1_512x512_grey"]["cpu_reference_1_thread_Mpix_s"] = None
+            try:
+                configs["C3_retarget_1080p_480_seams"] = config_c3({"device": local_rank}, hbm_peak)
+            except Exception as e:
+                configs["C3_retarget_1080p_480_seams"] = {"error": repr(e)}
+        # C4: 1080p batch, frames sharded over the ranks (weak: 2048 frames per GPU)
+        c4 = frames_config(ctx, timer, 1920, 1080, 3, 2048, 2048, 3, hbm_peak, SEED + 3, first_frame=rank * 2048)
+        c4["n_gpus"] = world
+        c4["Mpix_s"] *= world
+        c4["note"] = "2048 frames per GPU per launch; value = all ranks' pixels / max-over-ranks time"
+        configs["C4_batch_1080p"] = c4
+        # C5: one gigapixel image in row bands over the ranks (strong scaling), and on rank 0 alone for the baseline
+        c5 = gigapixel_config(ctx, timer, rank, world, hbm_peak, 5, rendezvous + "_c5")
+        if world > 1:
+            solo_timer = Timer(ctx, None, None)
+            one = gigapixel_config(ctx, solo_timer, 0, 1, hbm_peak, 5, rendezvous + "_c5solo") if rank == 0 else None
+            barrier()
+            if rank == 0:
+                c5["single_gpu_Mpix_s_same_box"] = one["Mpix_s"]
+                c5["strong_scaling_efficiency"] = c5["Mpix_s"] / (world * one["Mpix_s"])
+        configs["C5_gigapixel_row_bands"] = c5
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _, _ = cpu_reference_rate(wl)
+        cpu_baseline, _, _ = cpu_reference_rate(wl, blocksize=args.blocksize)
 
     if rank == 0:
         line = {
@@ -326,14 +528,13 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.workload == "gigapixel" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict({"workload": wl["desc"].replace("blocksize 8", "blocksize %d" % args.blocksize), "blocksize": args.blocksize, "edges": 0.5, "textures": 0.5,
-                            "kernel": args.kernel, "arithmetic": arithmetic(args.blocksize, args.kernel),
-                            "l2": "inputs+outputs per step exceed L2 (distinct frames)",
-                            "parallelism": "frames sharded, no collective" if args.workload != "gigapixel" else "row bands"},
-                           **cfg_extra),
+            "config": dict(shared_config(args, wl), **cfg_extra),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
+            "configs": configs,
         }
         print(json.dumps(line))
+    if runner is not None:
+        runner.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

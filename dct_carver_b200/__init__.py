@@ -29,6 +29,15 @@ ABI_SYMBOLS = [
     "dctc_synth_fill_dev", "dctc_synth_byte", "dctc_ipc_export", "dctc_ipc_open", "dctc_ipc_close",
     "dctc_dev_alloc", "dctc_dev_free", "dctc_host_alloc_pinned", "dctc_host_free_pinned", "dctc_memcpy_h2d",
     "dctc_memcpy_d2h", "dctc_memset_dev", "dctc_sync", "dctc_timer_begin", "dctc_timer_end",
+    # multi-GPU host layer (csrc/dctc_multi.cu)
+    "dctc_band_plan", "dctc_multi_create", "dctc_multi_destroy", "dctc_multi_device_count", "dctc_multi_context",
+    "dctc_multi_set_params", "dctc_multi_set_kernel", "dctc_multi_launch_count", "dctc_multi_energy_batch",
+    "dctc_multi_energy_bands", "dctc_multi_bands_create", "dctc_multi_bands_destroy", "dctc_multi_bands_geometry",
+    "dctc_multi_bands_upload", "dctc_multi_bands_synth", "dctc_multi_bands_energy", "dctc_multi_bands_download",
+    "dctc_multi_bands_energy_image", "dctc_rendezvous_allgather", "dctc_band_runner_create", "dctc_band_runner_geometry",
+    "dctc_band_runner_image_dev", "dctc_band_runner_energy_dev", "dctc_band_runner_synth", "dctc_band_runner_upload",
+    "dctc_band_runner_connect", "dctc_band_runner_barrier", "dctc_band_runner_energy", "dctc_band_runner_download",
+    "dctc_band_runner_energy_image", "dctc_band_runner_destroy", "dctc_pcie_probe",
 ]
 
 
@@ -114,6 +123,38 @@ def lib():
         "dctc_sync": (i32, [vp]),
         "dctc_timer_begin": (i32, [vp]),
         "dctc_timer_end": (i32, [vp, C.POINTER(f32)]),
+        "dctc_band_plan": (i32, [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "dctc_multi_create": (i32, [C.POINTER(vp), C.POINTER(i32), i32]),
+        "dctc_multi_destroy": (None, [vp]),
+        "dctc_multi_device_count": (i32, [vp]),
+        "dctc_multi_context": (vp, [vp, i32]),
+        "dctc_multi_set_params": (i32, [vp, C.POINTER(EnergyParameters)]),
+        "dctc_multi_set_kernel": (i32, [vp, i32]),
+        "dctc_multi_launch_count": (C.c_ulonglong, [vp]),
+        "dctc_multi_energy_batch": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, vp, sz]),
+        "dctc_multi_energy_bands": (i32, [vp, vp, i32, i32, i32, sz, vp, vp]),
+        "dctc_multi_bands_create": (i32, [vp, i32, i32, i32, C.POINTER(vp)]),
+        "dctc_multi_bands_destroy": (None, [vp]),
+        "dctc_multi_bands_geometry": (i32, [vp, i32, C.POINTER(i32), C.POINTER(i32)]),
+        "dctc_multi_bands_upload": (i32, [vp, vp, sz]),
+        "dctc_multi_bands_synth": (i32, [vp, u32, i32]),
+        "dctc_multi_bands_energy": (i32, [vp, i32]),
+        "dctc_multi_bands_download": (i32, [vp, vp]),
+        "dctc_multi_bands_energy_image": (i32, [vp, vp]),
+        "dctc_rendezvous_allgather": (i32, [C.c_char_p, i32, i32, vp, sz, vp, i32]),
+        "dctc_band_runner_create": (i32, [vp, C.c_char_p, i32, i32, i32, i32, i32, C.POINTER(vp)]),
+        "dctc_band_runner_geometry": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]),
+        "dctc_band_runner_image_dev": (vp, [vp]),
+        "dctc_band_runner_energy_dev": (vp, [vp]),
+        "dctc_band_runner_synth": (i32, [vp, u32, i32]),
+        "dctc_band_runner_upload": (i32, [vp, vp, sz]),
+        "dctc_band_runner_connect": (i32, [vp]),
+        "dctc_band_runner_barrier": (i32, [vp]),
+        "dctc_band_runner_energy": (i32, [vp, i32]),
+        "dctc_band_runner_download": (i32, [vp, vp]),
+        "dctc_band_runner_energy_image": (i32, [vp, vp]),
+        "dctc_band_runner_destroy": (None, [vp]),
+        "dctc_pcie_probe": (i32, [vp, sz, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -377,3 +418,144 @@ class Context:
             n = int(np.maximum(xmax - xmin + 1, 0).sum())
             band = band[:n]
         return band, xmin, xmax
+
+
+    def pcie_probe(self, nbytes=256 << 20, iters=8):
+        """Pinned host <-> device copy bandwidth (GB/s): H2D alone, D2H alone, per direction with both running."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(lib().dctc_pcie_probe(self._h, nbytes, iters, C.byref(a), C.byref(b), C.byref(c)), "dctc_pcie_probe")
+        return {"h2d_gbs": a.value, "d2h_gbs": b.value, "bidir_gbs_per_dir": c.value}
+
+
+def band_plan(h, world, rank, blocksize):
+    """(first row, rows, halo rows needed above, below) of `rank`'s band: dctc_band_plan."""
+    y0, rows, tn, bn = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _check(lib().dctc_band_plan(h, world, rank, blocksize, C.byref(y0), C.byref(rows), C.byref(tn), C.byref(bn)), "dctc_band_plan")
+    return y0.value, rows.value, tn.value, bn.value
+
+
+def rendezvous_allgather(name, rank, world, blob, timeout_ms=60000):
+    """All-gather of equal-sized byte strings over the ranks of one box through POSIX shared memory (no framework)."""
+    blob = bytes(blob)
+    mine = (C.c_ubyte * max(len(blob), 1)).from_buffer_copy(blob or b"\0")
+    out = (C.c_ubyte * max(len(blob) * world, 1))()
+    _check(lib().dctc_rendezvous_allgather(name.encode(), rank, world, mine, len(blob), out, timeout_ms), "dctc_rendezvous_allgather")
+    raw = bytes(out)
+    return [raw[i * len(blob):(i + 1) * len(blob)] for i in range(world)]
+
+
+class BandRunner:
+    """One rank's row band of a w x h image (one process per GPU): dctc_band_runner_*.  The halo rows are read from the
+    neighbour ranks' HBM by the energy kernel (CUDA IPC peer mappings exchanged through the C rendezvous)."""
+
+    def __init__(self, ctx, rendezvous, rank, world, w, h, ch):
+        self.ctx, self.rank, self.world, self.w, self.h, self.ch = ctx, rank, world, w, h, ch
+        self._r = C.c_void_p()
+        _check(lib().dctc_band_runner_create(ctx.handle, rendezvous.encode(), rank, world, w, h, ch, C.byref(self._r)),
+               "dctc_band_runner_create")
+        y0, rows, pitch = C.c_int(), C.c_int(), C.c_size_t()
+        _check(lib().dctc_band_runner_geometry(self._r, C.byref(y0), C.byref(rows), C.byref(pitch)), "dctc_band_runner_geometry")
+        self.y0, self.band_rows, self.pitch = y0.value, rows.value, pitch.value
+
+    def synth(self, seed, pattern=0):
+        _check(lib().dctc_band_runner_synth(self._r, seed, pattern), "dctc_band_runner_synth")
+
+    def upload(self, band_rows):
+        a = np.ascontiguousarray(band_rows, dtype=np.uint8)
+        _check(lib().dctc_band_runner_upload(self._r, _ptr(a), self.w * self.ch), "dctc_band_runner_upload")
+
+    def connect(self):
+        _check(lib().dctc_band_runner_connect(self._r), "dctc_band_runner_connect")
+
+    def barrier(self):
+        _check(lib().dctc_band_runner_barrier(self._r), "dctc_band_runner_barrier")
+
+    def step(self, sync=False):
+        _check(lib().dctc_band_runner_energy(self._r, int(sync)), "dctc_band_runner_energy")
+
+    def fetch(self):
+        out = np.empty((self.band_rows, self.w), np.float32)
+        _check(lib().dctc_band_runner_download(self._r, _ptr(out)), "dctc_band_runner_download")
+        return out
+
+    def energy_image(self):
+        out = np.empty((self.band_rows, self.w), np.uint8)
+        _check(lib().dctc_band_runner_energy_image(self._r, _ptr(out)), "dctc_band_runner_energy_image")
+        return out
+
+    def close(self):
+        if self._r:
+            lib().dctc_band_runner_destroy(self._r)
+            self._r = C.c_void_p()
+
+
+class Multi:
+    """All GPUs of the box from one process: dctc_multi_* (frames round-robin, row bands with peer halo reads)."""
+
+    def __init__(self, devices=None, blocksize=8, edges=0.5, textures=0.5, kernel=KERNEL_AUTO):
+        self._m = C.c_void_p()
+        if devices is None:
+            _check(lib().dctc_multi_create(C.byref(self._m), None, 0), "dctc_multi_create")
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(lib().dctc_multi_create(C.byref(self._m), arr, len(devices)), "dctc_multi_create")
+        self.n = lib().dctc_multi_device_count(self._m)
+        self.set_params(blocksize, edges, textures)
+        if kernel != KERNEL_AUTO:
+            _check(lib().dctc_multi_set_kernel(self._m, kernel), "dctc_multi_set_kernel")
+        self._bands = C.c_void_p()
+
+    def set_params(self, blocksize, edges, textures):
+        p = EnergyParameters(edges=edges, textures=textures, blocksize=blocksize)
+        _check(lib().dctc_multi_set_params(self._m, C.byref(p)), "dctc_multi_set_params")
+
+    @property
+    def launches(self):
+        return int(lib().dctc_multi_launch_count(self._m))
+
+    def energy_batch(self, imgs, out=None):
+        n, h, w, ch = imgs.shape
+        if out is None:
+            out = np.empty((n, h, w), np.float32)
+        _check(lib().dctc_multi_energy_batch(self._m, _ptr(imgs), n, h * w * ch, w, h, ch, w * ch, _ptr(out), h * w),
+               "dctc_multi_energy_batch")
+        return out
+
+    def energy_bands(self, img, want_image=False):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if img.ndim == 2:
+            img = img[:, :, None]
+        h, w, ch = img.shape
+        out = np.empty((h, w), np.float32)
+        im8 = np.empty((h, w), np.uint8) if want_image else None
+        _check(lib().dctc_multi_energy_bands(self._m, _ptr(img), w, h, ch, w * ch, _ptr(out), _ptr(im8) if want_image else None),
+               "dctc_multi_energy_bands")
+        return (out, im8) if want_image else out
+
+    # device-resident bands (bench)
+    def bands_create(self, w, h, ch):
+        self.bands_destroy()
+        _check(lib().dctc_multi_bands_create(self._m, w, h, ch, C.byref(self._bands)), "dctc_multi_bands_create")
+        self._bw, self._bh = w, h
+
+    def bands_synth(self, seed, pattern=0):
+        _check(lib().dctc_multi_bands_synth(self._bands, seed, pattern), "dctc_multi_bands_synth")
+
+    def bands_energy(self, sync=False):
+        _check(lib().dctc_multi_bands_energy(self._bands, int(sync)), "dctc_multi_bands_energy")
+
+    def bands_download(self):
+        out = np.empty((self._bh, self._bw), np.float32)
+        _check(lib().dctc_multi_bands_download(self._bands, _ptr(out)), "dctc_multi_bands_download")
+        return out
+
+    def bands_destroy(self):
+        if self._bands:
+            lib().dctc_multi_bands_destroy(self._bands)
+            self._bands = C.c_void_p()
+
+    def close(self):
+        self.bands_destroy()
+        if self._m:
+            lib().dctc_multi_destroy(self._m)
+            self._m = C.c_void_p()

@@ -254,7 +254,8 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
                                                                     float* __restrict__ mplane, size_t m_pitch,
                                                                     int* __restrict__ seam, int* __restrict__ seam_log,
                                                                     int* __restrict__ run_flag, int nst,
-                                                                    const __grid_constant__ CUtensorMap tmap, int use_tmap)
+                                                                    const __grid_constant__ CUtensorMap tmap, int use_tmap,
+                                                                    int* __restrict__ xlast)
 {
     // fallback of the incremental update (dctc_seam_incr_kernel): runs only when that kernel asked for a rebuild
     if (run_flag && *run_flag == 0) return;       // uniform over the cluster, before any cluster barrier
@@ -524,8 +525,12 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
         }
-        // back-track (warp 0 of CTA 0)
-        dp_backtrack(mplane, m_pitch, w, h, bi, seam, seam_log, win, lane);
+        if (xlast) {
+            // parallel back-track: the jump and trace kernels below take over from the seam's last-row column
+            if (lane == 0) { *xlast = bi; seam[h - 1] = bi; if (seam_log) seam_log[h - 1] = bi; }
+        } else {
+            dp_backtrack(mplane, m_pitch, w, h, bi, seam, seam_log, win, lane);   // serial walk by warp 0 of CTA 0
+        }
 #ifdef DCTC_SYNC_DEBUG
         if (tid == 0) {
             unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -533,6 +538,138 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
         }
 #endif
     }
+}
+
+// ---- parallel back-track (build_vpath without the h-step dependent chain) ---------------------------------------
+// The serial walk above is a chain of h dependent shared-memory reads (133 clk per row: 73 us of a 1080-row seam).  The
+// parent choice of a cell depends only on the cumulative map, not on the path, so the rows are cut into blocks of JB
+// rows (counted upwards from the last row) and, for EVERY column x of a block's bottom row, the column its path has at
+// the block's top row is computed in parallel: top-down, P_top[x] = x, P_y[x] = P_{y-1}[x + d_y(x)] with d_y(x) the
+// parent direction of (y, x) -- neighbours only, so a warp keeps a strip of 128 columns in registers and exchanges
+// the outer cells by shuffles, exactly like the seam DP (JB = 32 contaminated columns on each side, 64 published).
+// dctc_seam_jump_kernel: one warp per (strip, block), the whole grid busy for ~1 us; it stores the jump as an int8
+// offset.  dctc_seam_trace_kernel: one CTA per block; it follows the ceil((h-1)/32) jumps from the seam's last-row
+// column down to its own block (the jump entries a path can reach form a cone of 64*j+1 columns in block j, staged
+// into shared memory first), then walks its 32 rows like dp_backtrack does.  ~100 dependent steps instead of h.
+constexpr int JB = 32;
+
+__global__ void __launch_bounds__(128) dctc_seam_jump_kernel(const float* __restrict__ mplane, size_t m_pitch, int w, int h,
+                                                             int8_t* __restrict__ jump, size_t j_pitch, int strips)
+{
+    const int lane = threadIdx.x & 31;
+    const int strip = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (strip >= strips) return;
+    const int k = blockIdx.y;
+    const int yb = h - 1 - JB * k;                    // bottom row of the block
+    const int yt = max(yb - JB, 0);                   // top row
+    const int steps = yb - yt;
+    const float INF = __int_as_float(0x7f800000);
+    const int c0 = strip * 64 - JB + 4 * lane;        // this lane's four columns
+    const bool in_row = c0 >= 0 && c0 < w;            // (c0 is a multiple of 4 and the pitch covers round_up(w, 4))
+    const float* src = mplane + (size_t) yt * m_pitch + (in_row ? c0 : 0);
+    int P[4] = {c0, c0 + 1, c0 + 2, c0 + 3};
+    auto row = [&](float4 v) {                        // v = cumulative values of row y-1 -> P of row y
+        float m[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (!in_row || c0 + j >= w) m[j] = INF;   // outside the image: never a parent (range clipping)
+        float l = __shfl_up_sync(0xffffffffu, m[3], 1), r = __shfl_down_sync(0xffffffffu, m[0], 1);
+        int pl = __shfl_up_sync(0xffffffffu, P[3], 1), pr = __shfl_down_sync(0xffffffffu, P[0], 1);
+        if (lane == 0) l = INF;
+        if (lane == 31) r = INF;
+        int Q[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float a = j == 0 ? l : m[j - 1], b = m[j], c = j == 3 ? r : m[j + 1];
+            const int pa = j == 0 ? pl : P[j - 1], pb = P[j], pc = j == 3 ? pr : P[j + 1];
+            const bool p1 = b < a;                    // first strict minimum scanning x-1, x, x+1
+            const float best = p1 ? b : a;
+            const bool p2 = c < best;
+            Q[j] = p2 ? pc : (p1 ? pb : pa);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) P[j] = Q[j];
+    };
+    for (int i0 = 0; i0 < steps; i0 += 8) {           // eight independent loads in flight, then eight dependent steps
+        float4 pv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            pv[j] = __ldcg(reinterpret_cast<const float4*>(src + (size_t) min(i0 + j, steps - 1) * m_pitch));
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (i0 + j < steps) row(pv[j]);
+    }
+    if (lane >= JB / 4 && lane < 32 - JB / 4 && in_row) {
+        int8_t* dst = jump + (size_t) k * j_pitch + c0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (c0 + j < w) dst[j] = (int8_t) (P[j] - (c0 + j));
+    }
+}
+
+constexpr int TR_WIN = 72;                            // walk window: columns x-34 .. x+37 around the block's bottom column
+
+__global__ void __launch_bounds__(128) dctc_seam_trace_kernel(const float* __restrict__ mplane, size_t m_pitch, int w, int h,
+                                                              const int8_t* __restrict__ jump, size_t j_pitch,
+                                                              const int* __restrict__ xlast, int* __restrict__ seam,
+                                                              int* __restrict__ seam_log)
+{
+    extern __shared__ __align__(16) unsigned char tr_smem[];
+    __shared__ __align__(16) float win[JB][TR_WIN + 8];
+    __shared__ int xb_s;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int k = blockIdx.x;
+    const int x0 = *xlast;
+    // cone of block j: bottom columns x0 - 32 j .. x0 + 32 j, staged at offset 32 j (j - 1) + j
+    int8_t* cone = reinterpret_cast<int8_t*>(tr_smem);
+    for (int j = 0; j < k; j++) {
+        const int off = 32 * j * (j - 1) + j, lo = x0 - JB * j, n = 2 * JB * j + 1;
+        const int8_t* srcj = jump + (size_t) j * j_pitch;
+        for (int i = tid; i < n; i += 128) {
+            const int x = lo + i;
+            cone[off + i] = (x >= 0 && x < w) ? srcj[x] : (int8_t) 0;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int x = x0;
+        for (int j = 0; j < k; j++) x += cone[32 * j * (j - 1) + j + (x - (x0 - JB * j))];
+        xb_s = x;
+    }
+    __syncthreads();
+    int x = xb_s;
+    const int yb = h - 1 - JB * k, yt = max(yb - JB, 0), steps = yb - yt;
+    // window rows: win[i] = cumulative row yb-1-i, columns base .. base+TR_WIN-1 at win[i][4 + c - base]
+    const int max_base = (int) m_pitch - TR_WIN;
+    int base = (x - 34) & ~3;
+    base = base < 0 ? 0 : (base > max_base ? max_base : base);
+    for (int idx = tid; idx < steps * (TR_WIN / 4); idx += 128) {
+        const int i = idx / (TR_WIN / 4), c = idx - i * (TR_WIN / 4);
+        const float* src = mplane + (size_t) (yb - 1 - i) * m_pitch + base + 4 * c;
+        *reinterpret_cast<float4*>(&win[i][4 + 4 * c]) = __ldcg(reinterpret_cast<const float4*>(src));
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    const float INF = __int_as_float(0x7f800000);
+    // +inf sentinels left of column 0 and at column w (range clipping), so that the walk needs no bounds checks
+    if (lane < steps) {
+        if (base == 0) win[lane][3] = INF;
+        if (w - base >= 0 && w - base <= TR_WIN) win[lane][4 + w - base] = INF;
+    }
+    __syncwarp();
+    int mine = 0;
+    const float* wp = &win[0][4] + (x - base);
+    for (int i = 0; i < steps; i++) {
+        const float a = wp[-1], b = wp[0], c = wp[1];
+        const bool p1 = b < a;
+        const float best = p1 ? b : a;
+        const bool p2 = c < best;
+        const int d = p2 ? 1 : (p1 ? 0 : -1);
+        x += d;
+        wp += TR_WIN + 8 + d;
+        if (lane == i) mine = x;
+    }
+    if (lane < steps) { seam[yb - 1 - lane] = mine; if (seam_log) seam_log[yb - 1 - lane] = mine; }
 }
 
 // ---- incremental cumulative map (liblqr's update_mmap) -----------------------------------------------------------
@@ -1017,7 +1154,7 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         }
     }
     const size_t dp_smem = xrow_smem + sizeof(float) * ((size_t) nst * sr * wpc * 128 * P);
-    using dp_fn = void (*)(const float*, size_t, int, int, float*, size_t, int*, int*, int*, int, const CUtensorMap, int);
+    using dp_fn = void (*)(const float*, size_t, int, int, float*, size_t, int*, int*, int*, int, const CUtensorMap, int, int*);
     static const dp_fn table[3][3] = {{dctc_seam_dp_kernel<1, 0>, dctc_seam_dp_kernel<1, 16>, dctc_seam_dp_kernel<1, 32>},
                                       {dctc_seam_dp_kernel<2, 0>, dctc_seam_dp_kernel<2, 16>, dctc_seam_dp_kernel<2, 32>},
                                       {dctc_seam_dp_kernel<4, 0>, dctc_seam_dp_kernel<4, 16>, dctc_seam_dp_kernel<4, 32>}};
@@ -1053,8 +1190,19 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     if (incr_ok)   // dynamic + static shared memory can exceed the 48 KB default
         CK(ctx, cudaFuncSetAttribute(dctc_seam_incr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) incr_smem));
     if (!ctx->c_band) {
-        CK(ctx, cudaMalloc((void**) &ctx->c_band, sizeof(int) * 4));
-        CK(ctx, cudaMemsetAsync(ctx->c_band, 0, sizeof(int) * 4, ctx->stream));
+        CK(ctx, cudaMalloc((void**) &ctx->c_band, sizeof(int) * 8));
+        CK(ctx, cudaMemsetAsync(ctx->c_band, 0, sizeof(int) * 8, ctx->stream));
+    }
+    // parallel back-track (jump + trace kernels): needs the jump plane and a cone of jump entries in shared memory that
+    // grows with the square of the number of 32-row blocks; very tall images keep the serial walk of the DP kernel
+    const int nb = (h - 1 + JB - 1) / JB;
+    const size_t cone_smem = nb > 0 ? (size_t) 32 * (nb - 1) * (nb - 2 > 0 ? nb - 2 : 0) + nb + 16 : 16;
+    const bool par_bt = nb > 0 && cone_smem <= 200 * 1024 && !getenv("DCTC_SERIAL_BACKTRACK");
+    int* const xlast = par_bt ? ctx->c_band + 4 : nullptr;
+    if (par_bt) {
+        if (!ctx->c_dir) CK(ctx, cudaMalloc((void**) &ctx->c_dir, (size_t) nb * m_pitch));
+        if (cone_smem > 40 * 1024)
+            CK(ctx, cudaFuncSetAttribute(dctc_seam_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cone_smem));
     }
     for (int s = 0; s < n_seams; s++) {
         const int w_old = ctx->c_w;
@@ -1063,11 +1211,17 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
             // update_mmap + build_vpath: walk the changed cells only; the full rebuild below runs only if the walk gave up
             dctc_seam_incr_kernel<<<1, 32, incr_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, r,
                                                                      ctx->c_seam, log_s, ctx->c_band);
-            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, ctx->c_band, nst, tmap, use_tmap);
+            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, ctx->c_band, nst, tmap, use_tmap, nullptr);
             ctx->launches++;
         } else {
-            // build_mmap + build_vpath
-            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr, nst, tmap, use_tmap);
+            // build_mmap, then build_vpath: jump maps of all 32-row blocks in parallel, one trace CTA per block
+            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr, nst, tmap, use_tmap, xlast);
+            if (par_bt) {
+                const int js = (w_old + 63) / 64;
+                dctc_seam_jump_kernel<<<dim3((js + 3) / 4, nb), 128, 0, ctx->stream>>>(ctx->c_m, m_pitch, w_old, h, ctx->c_dir, m_pitch, js);
+                dctc_seam_trace_kernel<<<nb, 128, cone_smem, ctx->stream>>>(ctx->c_m, m_pitch, w_old, h, ctx->c_dir, m_pitch, xlast, ctx->c_seam, log_s);
+                ctx->launches += 2;
+            }
         }
 #ifdef DCTC_SYNC_DEBUG
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }

@@ -42,7 +42,7 @@ struct dctc_context {
     float* c_en = nullptr;         // device energy, pitch c_en_pitch floats (multiple of 4: 16-byte aligned rows)
     size_t c_en_pitch = 0;
     float* c_m = nullptr;          // cumulative map of the device seam DP (rebuilt per seam, read back by the back-track)
-    int8_t* c_dir = nullptr;       // (unused)
+    int8_t* c_dir = nullptr;       // jump plane of the parallel back-track: per 32-row block and bottom column, the path's column offset at the block top
     int* c_seam_log = nullptr;     // seams of dctc_carver_resize_width, n_seams * h
     size_t c_seam_log_cap = 0;
     // visibility map (lqr_carver_set_dump_vmaps, src/render.c:374): raw = original column of every current pixel,
@@ -52,7 +52,7 @@ struct dctc_context {
     int c_vs_depth = 0;
     bool c_dump_vmaps = false;
     int* c_seam = nullptr;         // h entries
-    int* c_band = nullptr;         // c_band[0]: 'rebuild the cumulative map from scratch' flag of the incremental seam DP (device)
+    int* c_band = nullptr;         // c_band[0]: 'rebuild the cumulative map from scratch' flag of the incremental seam DP; c_band[4]: last-row column of the current seam (device)
     bool c_incremental = false;    // device seam loop: update the cumulative map incrementally (dctc_carver_set_incremental)
     bool c_m_valid = false;        // the cumulative plane holds the map of the image before the last removal, compacted over that seam
     float* c_band_vals = nullptr;  // packed band values

@@ -218,6 +218,82 @@ int dctc_ipc_export(dctc_context *ctx, void *d_ptr, unsigned char handle[DCTC_IP
 int dctc_ipc_open(dctc_context *ctx, const unsigned char handle[DCTC_IPC_HANDLE_BYTES], void **d_peer_ptr);
 int dctc_ipc_close(dctc_context *ctx, void *d_peer_ptr);
 
+/* ---- multi-GPU: frames and row bands over the GPUs of one box ---------------------------
+ * The reference runs in one process on one CPU thread (src/render.c:310-315 is the C caller of the energy path);
+ * the path shards with a fixed halo and no collective: frame f -> device f mod G (BASELINE config 4), or one image
+ * split into row bands, device g owning rows [h*g/G, h*(g+1)/G) (config 5).  A band needs blocksize/2-1 rows from
+ * the band above and blocksize/2 rows from the band below (window offsets -b/2+1..b/2, src/render.c:146-147); the
+ * image's own edges replicate (src/render.c:122-132).  Halo rows are not exchanged: the energy kernel of a band
+ * loads them straight from the neighbour's HBM over NVLink (peer pointers). */
+
+/* Band geometry of `rank` out of `world`: first row, row count, halo rows needed above / below.
+ * DCTC_ERR_INVALID if some band would be thinner than blocksize/2 rows (it could not serve its neighbours' halos). */
+int dctc_band_plan(int h, int world, int rank, int blocksize, int *y0, int *rows, int *top_need, int *bot_need);
+
+/* -- one process drives all devices (what a C caller like render() would link against) -- */
+typedef struct dctc_multi dctc_multi;
+typedef struct dctc_multi_bands dctc_multi_bands;
+/* One context (own streams) per entry of devices[] (NULL: every visible device); peer access is enabled between all
+ * pairs.  The same device may be listed more than once (the bands then share one GPU; used by single-GPU tests). */
+int dctc_multi_create(dctc_multi **m, const int *devices, int n_devices);
+void dctc_multi_destroy(dctc_multi *m);
+int dctc_multi_device_count(const dctc_multi *m);
+dctc_context *dctc_multi_context(dctc_multi *m, int i);
+int dctc_multi_set_params(dctc_multi *m, const DctcEnergyParameters *params);
+int dctc_multi_set_kernel(dctc_multi *m, int kernel);
+unsigned long long dctc_multi_launch_count(const dctc_multi *m);
+/* dctc_energy_batch over all devices: frame f is processed by device f mod G, every device with its own
+ * H2D / kernel / D2H pipeline, one host thread per device.  Same arguments and result as dctc_energy_batch. */
+int dctc_multi_energy_batch(dctc_multi *m, const uint8_t *imgs, int n_frames, size_t frame_stride_bytes, int w, int h,
+                            int channels, size_t pitch_bytes, float *out, size_t out_frame_stride);
+/* One host image -> row bands over the devices -> the full energy map `out` (w*h floats, may be NULL) and / or the
+ * 8-bit energy image `image_out` (w*h bytes, may be NULL; K3 with the (min, max) pair reduced over the bands).
+ * Bit-identical to dctc_energy_full / dctc_carver_energy_image on one device. */
+int dctc_multi_energy_bands(dctc_multi *m, const uint8_t *img, int w, int h, int channels, size_t pitch_bytes,
+                            float *out, uint8_t *image_out);
+/* The same in steps, bands resident on the devices (bench.py times dctc_multi_bands_energy). */
+int dctc_multi_bands_create(dctc_multi *m, int w, int h, int channels, dctc_multi_bands **bands);
+void dctc_multi_bands_destroy(dctc_multi_bands *bands);
+int dctc_multi_bands_geometry(const dctc_multi_bands *bands, int g, int *y0, int *rows);
+int dctc_multi_bands_upload(dctc_multi_bands *bands, const uint8_t *img, size_t pitch_bytes);
+int dctc_multi_bands_synth(dctc_multi_bands *bands, uint32_t seed, int pattern);
+int dctc_multi_bands_energy(dctc_multi_bands *bands, int sync);
+int dctc_multi_bands_download(dctc_multi_bands *bands, float *out);
+int dctc_multi_bands_energy_image(dctc_multi_bands *bands, uint8_t *out);
+
+/* -- one process per GPU (bench.py under torchrun): each rank owns one band -- */
+typedef struct dctc_band_runner dctc_band_runner;
+/* All-gather of `bytes` bytes per rank through a POSIX shared-memory segment named after `name` (unique per
+ * exchange); also a barrier.  DCTC_ERR_STATE on timeout (timeout_ms <= 0: wait forever). */
+int dctc_rendezvous_allgather(const char *name, int rank, int world, const void *mine, size_t bytes, void *all,
+                              int timeout_ms);
+/* Allocates this rank's band of a w x h image on the context's device.  `rendezvous` names the job (e.g. the
+ * launcher's port + run id); the collective calls below exchange through "<rendezvous>_<sequence number>". */
+int dctc_band_runner_create(dctc_context *ctx, const char *rendezvous, int rank, int world, int w, int h, int channels,
+                            dctc_band_runner **runner);
+int dctc_band_runner_geometry(const dctc_band_runner *runner, int *y0, int *rows, size_t *pitch_bytes);
+void *dctc_band_runner_image_dev(dctc_band_runner *runner);
+float *dctc_band_runner_energy_dev(dctc_band_runner *runner);
+int dctc_band_runner_synth(dctc_band_runner *runner, uint32_t seed, int pattern);
+int dctc_band_runner_upload(dctc_band_runner *runner, const uint8_t *band_rows, size_t pitch_bytes);
+/* COLLECTIVE: exports the band buffer as a CUDA IPC handle, all-gathers the handles and maps the neighbours' bands.
+ * The band must hold its content: the exchange is the barrier between "filled" and "neighbours may read". */
+int dctc_band_runner_connect(dctc_band_runner *runner);
+/* COLLECTIVE: stream sync + barrier (e.g. between re-filling the bands and the next energy launch). */
+int dctc_band_runner_barrier(dctc_band_runner *runner);
+/* K1 on this rank's band, halo rows loaded from the neighbours' HBM by the kernel itself. */
+int dctc_band_runner_energy(dctc_band_runner *runner, int sync);
+int dctc_band_runner_download(dctc_band_runner *runner, float *out_rows);
+/* COLLECTIVE: K3 over the sharded map ((min, max) all-gathered and reduced on the host), this rank's rows. */
+int dctc_band_runner_energy_image(dctc_band_runner *runner, uint8_t *out_rows);
+/* COLLECTIVE: barrier, then frees the band (no rank frees memory a neighbour's kernel may still be reading). */
+void dctc_band_runner_destroy(dctc_band_runner *runner);
+
+/* Pinned host <-> device copy bandwidth of this context's device in GB/s: H2D alone, D2H alone, and per direction
+ * with both running (the ceiling of the host-buffer entry points; bench.py reports it next to `e2e`). */
+int dctc_pcie_probe(dctc_context *ctx, size_t bytes, int iters, double *h2d_gbs, double *d2h_gbs,
+                    double *bidir_gbs_per_dir);
+
 /* ---- raw device memory helpers so that C / ctypes callers need no other CUDA binding -------------------- */
 int dctc_dev_alloc(dctc_context *ctx, void **d_ptr, size_t bytes);
 int dctc_dev_free(dctc_context *ctx, void *d_ptr);

@@ -75,7 +75,26 @@ def test_carver_state_errors(ctx):
     c2.carver_load(np.zeros((4, 6, 3), np.uint8))
     bad = np.array([0, 1, 6, 2], np.int32)
     assert L.dctc_carve_and_update(c2.handle, bad.ctypes.data, None, None, None) == dc.ERR_STATE
+    # a disconnected seam (|dx| > 1) is not a liblqr seam with delta_x = 1 (src/render.c:313): refused, nothing carved
+    jump = np.array([0, 1, 3, 3], np.int32)
+    assert L.dctc_carve_and_update(c2.handle, jump.ctypes.data, None, None, None) == dc.ERR_INVALID
+    assert c2.carver_size() == (6, 4)
     c2.close()
+
+
+@pytest.mark.parametrize("b2,wts2", [(16, (0.5, 0.5)), (8, (0.8, 0.2)), (2, (0.5, 0.5))])
+def test_set_params_rebuilds_the_map_of_a_loaded_session(ctx, b2, wts2):
+    """lqr_carver_set_energy_function invalidates liblqr's energy map; here a parameter change with a session loaded
+    rebuilds the resident map, so band radius / stride and map always belong to the same operator."""
+    img = ol.synth_image(90, 60, 3, 41, 0)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.carver_load(img)
+    ctx.set_params(b2, *wts2)
+    assert np.array_equal(ctx.carver_energy(), ctx.energy_full(img))
+    seam = np.full(60, 33, np.int32)
+    ctx.carve_and_update(seam)
+    assert np.array_equal(ctx.carver_energy(), ctx.energy_full(carve_host(img, seam)))
+    ctx.set_params(8, 0.5, 0.5)
 
 
 def test_per_pixel_symbol_serves_host_mirror(ctx):
@@ -119,9 +138,13 @@ def test_gpu_retarget_equals_naive_loop_fed_with_gpu_energy(ctx, b, wts, device_
 
 def test_gpu_retarget_seams_vs_reference_energy(ctx):
     """Seams chosen from the GPU (FP32) energies vs from the reference's double-precision energies: bit-exact until
-    a near-tie in the cumulative map flips (north_star: 'bit-exact wherever energy ties do not flip')."""
+    a near-tie in the cumulative map flips (north_star: 'bit-exact wherever energy ties do not flip').  The first
+    diverging seam must BE such a tie: both loops hold the same image at that point, so with delta = the largest
+    difference the energy tolerance and the FP32 sums can make along one seam, the seam the GPU loop removed costs at
+    most 2*delta more than the reference's seam when both are priced with the reference's energies."""
     from dct_carver_b200 import host
     img = ol.synth_image(160, 100, 3, 77, 0)
+    h = img.shape[0]
     ctx.set_params(8, 0.5, 0.5)
     got = host.render(img, -30, 8, 0.5, 0.5, ctx=ctx)
     seams_ref, _ = _naive(img, 8, 0.5, 0.5, 30, energy=lambda cur: ol.best_energy(cur, 8, 0.5, 0.5))
@@ -129,6 +152,18 @@ def test_gpu_retarget_seams_vs_reference_energy(ctx):
     lead = same.index(False) if False in same else len(same)
     print("identical leading seams: %d / %d" % (lead, len(same)))
     assert lead >= 1
+    if lead < len(same):
+        cur = img
+        for k in range(lead):
+            cur = carve_host(cur, seams_ref[k])
+        en = ol.best_energy(cur, 8, 0.5, 0.5).astype(np.float64)
+        rows = np.arange(h)
+        cost_gpu = en[rows, got["seams"][lead]].sum()
+        cost_ref = en[rows, seams_ref[lead]].sum()
+        delta = h * (ol.ABS_TOL + ol.REL_TOL * en.max()) + h * 2.0 ** -23 * max(cost_gpu, cost_ref)
+        print("first divergence at seam %d: cost %.9g (GPU seam) vs %.9g (reference seam), bound %.3g" % (lead, cost_gpu, cost_ref, 2 * delta))
+        assert cost_ref <= cost_gpu + 2 * delta      # the reference's seam is (nearly) optimal for its own energies
+        assert cost_gpu <= cost_ref + 2 * delta      # ... and the GPU's seam ties with it within the tolerance
 
 
 def test_gpu_retarget_height_and_energy_image(ctx):
@@ -194,18 +229,27 @@ def test_device_seam_loop_incremental_map_equals_rebuild(ctx, b, ch, w, h, n, pa
     assert 0 <= rebuilds < n
 
 
+@pytest.mark.parametrize("flat", [True, False])
+@pytest.mark.parametrize("w,h", [(203, 77), (204, 77), (144, 40), (1920, 70)])
 @pytest.mark.parametrize("side", ["left", "right"])
-def test_device_seam_loop_hugs_the_image_border(ctx, side):
-    """Only the outermost column has zero energy (its edge-replicated window is flat), so every seam runs down the
-    image border: exercises the range clipping of the seam DP and of the back-track windows (+inf sentinels left of
-    column 0 and at column w) against the host carver."""
+def test_device_seam_loop_hugs_the_image_border(ctx, side, w, h, flat):
+    """The outermost column has the lowest energy, so every seam runs down the image border: exercises the range
+    clipping of the seam DP and of the back-track windows (+inf sentinels left of column 0 and at column w) against
+    the host carver.  flat: the border columns are constant (zero energy); otherwise they carry a vertical dither whose
+    amplitude grows away from the border (non-zero cumulative values, so a missing sentinel would win the comparison).
+    Widths that are a multiple of 4 and >= 144 make the cumulative plane's pitch equal to the width: the window of the
+    first seam then ends exactly at column w (the right sentinel sits in the window row's tail pad)."""
     from dct_carver_b200 import host
-    w, h, n = 203, 77, 4
+    n = 4
     img = ol.synth_image(w, h, 3, 909, 0)
-    if side == "right":
-        img[:, -4:, :] = 128
+    k = 12
+    cols = np.arange(w - k, w) if side == "right" else np.arange(k - 1, -1, -1)
+    if flat:
+        # window offsets are -3..+4: 4 flat columns on the right / 5 on the left make exactly the border column flat
+        img[:, cols[-(4 if side == "right" else 5):], :] = 128
     else:
-        img[:, :5, :] = 128
+        amp = np.arange(k, 0, -1)                       # 12 ... 1 towards the border
+        img[:, cols, :] = (128 + (np.arange(h)[:, None] & 1) * amp[None, :])[:, :, None]
     ctx.set_params(8, 0.5, 0.5)
     want = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, device_loop=False)
     ctx.set_params(8, 0.5, 0.5)
