@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "dctc_version", "dctc_device_count", "dctc_stream", "dctc_launch_count",
     "dctc_energy_full", "dctc_energy_full_dev", "dctc_energy_batch_dev", "dctc_energy_band_dev", "dctc_energy_batch",
     "dctc_carver_load", "dctc_carver_width", "dctc_carver_height", "dctc_carver_energy", "dctc_carve_and_update",
-    "dctc_carver_image", "dctc_carver_resize_width", "dctc_carver_set_incremental", "dctc_carver_rebuild_count", "dctc_pixel_energy",
+    "dctc_carver_image", "dctc_carver_resize_width", "dctc_carver_enlarge_width", "dctc_carver_set_incremental", "dctc_carver_rebuild_count", "dctc_pixel_energy",
     "dctc_energy_minmax_dev", "dctc_energy_image_dev", "dctc_carver_energy_image", "dctc_preview_energy",
     "dctc_carver_set_dump_vmaps", "dctc_carver_vmap", "dctc_carver_paint_seams",
     "dctc_synth_fill_dev", "dctc_synth_byte", "dctc_ipc_export", "dctc_ipc_open", "dctc_ipc_close",
@@ -98,6 +98,7 @@ def lib():
         "dctc_carve_and_update": (i32, [vp, vp, vp, vp, vp]),
         "dctc_carver_image": (i32, [vp, vp]),
         "dctc_carver_resize_width": (i32, [vp, i32, vp]),
+        "dctc_carver_enlarge_width": (i32, [vp, i32, vp]),
         "dctc_carver_rebuild_count": (i32, [vp]),
         "dctc_carver_set_incremental": (i32, [vp, i32]),
         "dctc_energy_minmax_dev": (i32, [vp, vp, C.c_size_t, i32, i32, vp]),
@@ -339,6 +340,15 @@ class Context:
         seams = np.empty((n_seams, h), np.int32)
         _check(lib().dctc_carver_resize_width(self._h, int(n_seams), _ptr(seams) if n_seams else None),
                "dctc_carver_resize_width")
+        return seams
+
+    def carver_enlarge_width(self, n_seams):
+        """lqr_carver_resize to a larger width on the device: returns the n_seams seams (as carver_resize_width does);
+        the session continues on the enlarged image."""
+        w, h = self.carver_size()
+        seams = np.empty((n_seams, h), np.int32)
+        _check(lib().dctc_carver_enlarge_width(self._h, int(n_seams), _ptr(seams) if n_seams else None),
+               "dctc_carver_enlarge_width")
         return seams
 
     def carver_set_incremental(self, on):

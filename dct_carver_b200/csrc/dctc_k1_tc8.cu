@@ -61,9 +61,7 @@ struct RawGeom {
 };
 
 struct alignas(128) TcSmem {
-    __half B[8][64 * 16];            // Tz as UMMA K-major no-swizzle operands: [0] Bh, [1] Bl, [2]/[3] the K-swapped copies,
-                                     // [4..7] the same with the k2 = 0 columns zeroed (k1 = 0: the DC coefficient (0,0) is skipped,
-                                     // src/dct.c:101 -- its accumulators come out as exact zeros and the fold needs no special case)
+    __half B[4][64 * 16];            // Tz as UMMA K-major no-swizzle operands: [0] Bh, [1] Bl, [2]/[3] the K-swapped copies
     float2 L[2][4][LWP];             // luma of two groups: [buffer][row pair][column], .x = even row
     uint8_t Raw[3][8 * RawGeom<3>::ROW];
     float park[16][MW];              // non-uniform weights: per-row quantities of the class rule parked by the consumers
@@ -168,17 +166,14 @@ __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t r0, uint32_t
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
-// 32 consecutive TMEM columns -> registers, asynchronous: the registers are valid after tmem_ld_wait(v)
-__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32])
+__device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t (&v)[64])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr) : "memory");
-}
-// Waits for every tcgen05.ld this thread has issued (ptxas turns it into a scoreboard wait in front of the first use)
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32])
-{
-    (void) v;
+                 : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                 : "r"(taddr + 32u));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
@@ -406,17 +401,18 @@ struct TcFold<true> {   // edges == textures: only the maximum matters
 #pragma unroll
         for (int i = 0; i < 8; i++) m[i] = 0.0f;
     }
-    // rows 4H .. 4H+3 of the k1 tile: v[ii * 8 + k2]
-    template <int K1, int H>
-    __device__ __forceinline__ void add_half(const uint32_t (&v)[32])
+    template <int K1>
+    __device__ __forceinline__ void add(const uint32_t (&v)[64])
     {
 #pragma unroll
-        for (int ii = 0; ii < 4; ii++) {
-            float t = m[4 * H + ii];   // the (0,0) accumulator of the k1 = 0 tile is an exact zero (DC-zeroed operand)
+        for (int i = 0; i < 8; i++) {
+            float t = m[i];
+            if (K1 != 0) t = fmaxf(t, fabsf(__uint_as_float(v[i * 8])));   // (0,0) is skipped (src/dct.c:101)
+            t = fmaxf(t, fabsf(__uint_as_float(v[i * 8 + 1])));
 #pragma unroll
-            for (int k2 = 0; k2 < 8; k2 += 2)
-                t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[ii * 8 + k2])), fabsf(__uint_as_float(v[ii * 8 + k2 + 1]))));
-            m[4 * H + ii] = t;
+            for (int k2 = 2; k2 < 8; k2 += 2)
+                t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[i * 8 + k2])), fabsf(__uint_as_float(v[i * 8 + k2 + 1]))));
+            m[i] = t;
         }
     }
     __device__ __forceinline__ float result(int i, float we, float wt) const { (void) we; return m[i] * wt; }
@@ -441,24 +437,23 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
         for (int i = 0; i < 8; i++) z[i] = 0.0f;
         flags = 0u;
     }
-    template <int K1, int H>
-    __device__ __forceinline__ void add_half(const uint32_t (&v)[32])
+    template <int K1>
+    __device__ __forceinline__ void add(const uint32_t (&v)[64])
     {
 #pragma unroll
-        for (int ii = 0; ii < 4; ii++) {
-            const int i = 4 * H + ii;
+        for (int i = 0; i < 8; i++) {
             if (K1 == 0) {
-                const float a = fabsf(__uint_as_float(v[ii * 8 + 1]));
+                const float a = fabsf(__uint_as_float(v[i * 8 + 1]));
                 float mm = -1.0f;
 #pragma unroll
-                for (int k2 = 2; k2 < 8; k2++) mm = fmaxf(mm, fabsf(__uint_as_float(v[ii * 8 + k2])));
+                for (int k2 = 2; k2 < 8; k2++) mm = fmaxf(mm, fabsf(__uint_as_float(v[i * 8 + k2])));
                 park[i * MW] = fmaxf(a, mm);
                 if (mm >= a) flags |= 1u << i;
             } else {
-                if (K1 == 1) park[(8 + i) * MW] = fabsf(__uint_as_float(v[ii * 8]));
-                else z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[ii * 8])));
+                if (K1 == 1) park[(8 + i) * MW] = fabsf(__uint_as_float(v[i * 8]));
+                else z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[i * 8])));
 #pragma unroll
-                for (int k2 = 1; k2 < 8; k2++) z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[ii * 8 + k2])));
+                for (int k2 = 1; k2 < 8; k2++) z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[i * 8 + k2])));
             }
         }
     }
@@ -471,43 +466,27 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
     }
 };
 
-// The consumers' part of one step, software-pipelined in half tiles (rows 0-3 = accumulator columns 0-31, rows 4-7 =
-// columns 32-63): a tcgen05.ld of 32 columns is always in flight while the other half is folded, so the TMEM read
-// latency (~180 clk per tile when a tile was loaded and then folded; 20 % of the consumers' time in the round-1
-// profile) hides behind the FMNMX3 chains.  consume_pair handles the tiles k1 = 2q (accumulator tile 0) and 2q+1
-// (tile 1).  It is entered with the load of the first half of tile 0 in flight; KC = 0 marks the pair (k1 = 0, 1), whose
-// folds treat the DC coefficient and the edge atoms specially.  The pairs q = 1..3 run as a real loop (not unrolled) so
-// that the two 32-register blocks keep their registers from tile to tile.
-template <int KC, bool UNIFORM>
-__device__ __forceinline__ void consume_pair(TcSmem& s, TcFold<UNIFORM>& f, uint32_t tmem_lane, uint32_t (&lo)[32], uint32_t (&hi)[32],
-                                             uint32_t parity, bool last, long long* g_tt_acc)
+template <int K1, bool UNIFORM>
+__device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32_t tmem_lane, bool lane0, long long* g_tt_acc)
 {
     (void) g_tt_acc;
-    constexpr int KA = KC == 0 ? 0 : 2, KB = KC == 0 ? 1 : 3;   // fold variants: k1 = 0, k1 = 1, k1 >= 2
-    // ---- accumulator tile 0 ----
-    { TT_T0(); tmem_ld_wait(lo); TT_ACC(1, 2); }              // rows 0-3 have landed
-    tmem_ld_x32(tmem_lane + TM_D + 32u, hi);                  // rows 4-7 in flight ...
-    f.template add_half<KA, 0>(lo);                           // ... while rows 0-3 are folded
-    { TT_T0(); tmem_ld_wait(hi); TT_ACC(1, 2); }
-    tc_fence_before();
-    bar_tile_arrive(0);                                       // tile 0 is in registers: the MMA warp may overwrite it
-    { TT_T0(); mbar_wait(smem_u32(&s.bar_d_full[1]), parity); TT_ACC(1, 1); }
-    tc_fence_after();
-    tmem_ld_x32(tmem_lane + TM_D + 64u, lo);                  // first half of tile 1 in flight ...
-    f.template add_half<KA, 1>(hi);                           // ... while rows 4-7 are folded
-    // ---- accumulator tile 1 ----
-    { TT_T0(); tmem_ld_wait(lo); TT_ACC(1, 2); }
-    tmem_ld_x32(tmem_lane + TM_D + 96u, hi);
-    f.template add_half<KB, 0>(lo);
-    { TT_T0(); tmem_ld_wait(hi); TT_ACC(1, 2); }
-    tc_fence_before();
-    bar_tile_arrive(1);
-    if (!last) {
-        { TT_T0(); mbar_wait(smem_u32(&s.bar_d_full[0]), parity ^ 1u); TT_ACC(1, 1); }
-        tc_fence_after();
-        tmem_ld_x32(tmem_lane + TM_D, lo);                    // first half of the next pair's tile 0
+    constexpr int b = K1 & 1, q = K1 >> 1;
+    {
+        TT_T0();
+        mbar_wait(smem_u32(&s.bar_d_full[b]), (uint32_t) (q & 1));
+        TT_ACC(1, K1 == 0 ? 0 : 1);
     }
-    f.template add_half<KB, 1>(hi);
+    tc_fence_after();
+    uint32_t v[64];
+    {
+        TT_T0();
+        tmem_ld_x64(tmem_lane + TM_D + 64u * b, v);
+        TT_ACC(1, 2);
+    }
+    tc_fence_before();
+    (void) lane0;
+    bar_tile_arrive(b);
+    f.template add<K1>(v);
 }
 
 // Persistent kernel: two CTAs per SM (256 TMEM columns each), work items = (frame, segment, strip) handed out by an
@@ -527,11 +506,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
     // Toeplitz operands: Tz[n = i*8 + k2][k] = B8[k2][r - i] with window row r = k (normal) or k ^ 8 (K-swapped)
     {
         uint16_t* Bq = reinterpret_cast<uint16_t*>(&s.B[0][0]);
-        for (int idx = tid; idx < 8 * 1024; idx += NTHREADS) {
+        for (int idx = tid; idx < 4 * 1024; idx += NTHREADS) {
             const int v = idx >> 10, n = (idx >> 4) & 63, k = idx & 15;
             const int i = n >> 3, k2 = n & 7;
             const int c = ((v & 2) ? (k ^ 8) : k) - i;
-            const uint16_t val = (c >= 0 && c < 8 && !((v & 4) && k2 == 0)) ? DCTC_TC_BASIS8[v & 1][k2 * 8 + c] : (uint16_t) 0;
+            const uint16_t val = (c >= 0 && c < 8) ? DCTC_TC_BASIS8[v & 1][k2 * 8 + c] : (uint16_t) 0;
             Bq[v * 1024 + (n >> 3) * 128 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7)] = val;
         }
     }
@@ -605,27 +584,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         // ===== consumers =====
         const int px = tid - 128;
         const int gx = x0 + px;
+        const bool lane0 = (tid & 31) == 0;
         for (int st = 0; st < nsteps; st++) {
             TcFold<UNIFORM> f;
             f.init();
             f.set_park(&s.park[0][px]);
             bar_step_sync();                                  // the MMA warp has started this step
-            uint32_t vlo[32], vhi[32];
-            {
-                TT_T0();
-                mbar_wait(smem_u32(&s.bar_d_full[0]), 0u);
-                TT_ACC(1, 0);
-            }
-            tc_fence_after();
-            tmem_ld_x32(tmem_lane + TM_D, vlo);
-            if (UNIFORM) {   // every tile folds alike: one rolled loop, the two 32-register blocks never move
-#pragma unroll 1
-                for (int q = 0; q < 4; q++) consume_pair<1, UNIFORM>(s, f, tmem_lane, vlo, vhi, (uint32_t) (q & 1), q == 3, g_tt_acc);
-            } else {
-                consume_pair<0, UNIFORM>(s, f, tmem_lane, vlo, vhi, 0u, false, g_tt_acc);
-#pragma unroll 1
-                for (int q = 1; q < 4; q++) consume_pair<1, UNIFORM>(s, f, tmem_lane, vlo, vhi, (uint32_t) (q & 1), q == 3, g_tt_acc);
-            }
+            consume_k1<0, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<1, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<2, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<3, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<4, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<5, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<6, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
+            consume_k1<7, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
             const int gy = y0 + 8 * st;
             if (gx < a.w) {
                 float* __restrict__ o = out + (size_t) gy * a.out_pitch + gx;
@@ -672,11 +644,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
                 if (elect_one()) {
                     const uint32_t d = tmem + TM_D + 64u * b;
                     const uint32_t ah = tmem + TM_A + (uint32_t) k1 * 16u, al = ah + 8u;
-                    // k1 = 0 multiplies with the DC-zeroed copies of Tz (4 operand copies = 512 descriptor units further)
-                    const uint64_t bhk = k1 == 0 ? bh + 512 : bh, blk = k1 == 0 ? bl + 512 : bl;
-                    mma_ts(d, ah, bhk, idesc, 0u);
-                    mma_ts(d, al, bhk, idesc | (1u << 13), 1u);   // A negated: the ring holds -lo
-                    mma_ts(d, ah, blk, idesc, 1u);
+                    mma_ts(d, ah, bh, idesc, 0u);
+                    mma_ts(d, al, bh, idesc | (1u << 13), 1u);   // A negated: the ring holds -lo
+                    mma_ts(d, ah, bl, idesc, 1u);
                     mma_commit(smem_u32(&s.bar_d_full[b]));
                     if (k1 == 3 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free_lo));
                     if (k1 == 7 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free));   // waited on by the producers of group st+2

@@ -134,6 +134,13 @@ __device__ __forceinline__ float4 dp_ld_cluster_v4(uint32_t ra)
     asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
     return v;
 }
+// 16 bytes into a peer CTA's shared memory; their arrival is counted on the peer's mbarrier (complete_tx), so the
+// receiver needs no fence and no cluster barrier: it waits on its own mbarrier for the bytes it expects
+__device__ __forceinline__ void dp_st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(remote_mbar) : "memory");
+}
 __device__ __forceinline__ void dp_st_cluster_f32(uint32_t ra, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory"); }
 __device__ __forceinline__ void dp_st_cluster_s32(uint32_t ra, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(ra), "r"(v) : "memory"); }
 
@@ -270,6 +277,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
     extern __shared__ __align__(128) float xrow[]; // two exchange rows of (warps per CTA * WOUT) floats, double buffered;
                                                   // TMA: followed by warps x nst stages x DP_SR rows x STRIP energies
     __shared__ __align__(8) unsigned long long ebar[DP_MAXW][DP_NST_MAX];
+    __shared__ __align__(8) unsigned long long hbar[DP_MAXW][2];   // halo exchange: per warp and slot, counts the neighbours' bytes
     __shared__ float red_v[DP_CL * DP_MAXW];      // per-strip minima, gathered in CTA 0 through distributed shared memory
     __shared__ int red_i[DP_CL * DP_MAXW];
     __shared__ __align__(16) float win[2][32][DP_WINP];
@@ -341,15 +349,20 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
                          ::"r"(dst), "l"(src), "r"((uint32_t) tbytes), "r"(bar) : "memory");
         }
     };
-    if (TMA) {
-        if (lane == 0) {
+    if (lane == 0) {
+        if (TMA) {
 #pragma unroll
             for (int st = 0; st < DP_NST_MAX; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&ebar[tid >> 5][st])) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncwarp();
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&hbar[tid >> 5][0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&hbar[tid >> 5][1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (TMA) {
         for (int ch = 0; ch < nst && ch < nchunks; ch++) issue_chunk(ch, ch);
     }
+    dp_cluster_sync();   // once: every CTA's halo mbarriers exist before a neighbour's first st.async can arrive
 
     float4 cur[DP_P], e[PF][DP_P];
 #pragma unroll
@@ -377,6 +390,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
 #pragma unroll
     for (int g = 0; g < DP_P; g++) any_mask |= inf_mask[g];
     int xb = 0;
+    int hround = 0;                                  // halo exchanges done: slot = hround & 1, mbarrier parity = (hround >> 1) & 1
     int c_ch = 0, c_st = 0;                          // chunk being consumed, its stage and mbarrier parity
     uint32_t c_par = 0;
     uint32_t stg_s = 0;                              // shared-space address of this lane's cells in the current chunk
@@ -467,22 +481,47 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
                 if (TMA && kk % SRD == SRD - 1) chunk_end();
             });
         }
-        // exchange the last row of the block: every warp publishes its central cells, then reloads its whole strip
+        // Exchange the last row of the block with the two neighbouring strips only: the outer 32 published cells on each
+        // side go straight into the neighbour warp's halo slot (st.async into its CTA's shared memory, completion counted
+        // on ITS mbarrier), then this warp waits for the 2 x 128 bytes it expects itself.  No cluster-wide barrier and no
+        // memory fence: the release/acquire cluster barrier used before carried MEMBAR.ALL.GPU + CCTL.IVALL, i.e. it also
+        // waited for the block's global stores of the cumulative plane (40 % of the kernel's stall samples).
+        // Slot = block parity: a neighbour can be at most one block ahead, it needs this warp's row to go further.
         if (yb + DP_R < h && !(DP_EXP & 4)) {
-            float* xr = xrow + xb * xlen;                 // this CTA's segment: columns [rank * xlen, (rank + 1) * xlen)
-            if (central) {
-#pragma unroll
-                for (int g = 0; g < DP_P; g++) *reinterpret_cast<float4*>(xr + (c0 + 4 * g - (int) rank * xlen)) = cur[g];
+            const int wl = tid >> 5;                          // warp inside the CTA
+            float* halo = xrow + (wl * 2 + xb) * 64;          // [0,32): cells left of the published range, [32,64): right
+            const uint32_t my_bar = dp_smem_u32(&hbar[wl][xb]);
+            if (lane == 0) {
+                const uint32_t expect = (warp > 0 ? 128u : 0u) + (warp < nwarps - 1 ? 128u : 0u);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(my_bar), "r"(expect) : "memory");
             }
-            dp_cluster_sync();
+            if (lane >= HL && lane < 2 * HL && warp > 0) {                        // my leftmost 32 published cells
+                const int nw = warp - 1;
+                const uint32_t nrank = (uint32_t) (nw / wpc);
+                const int nwl = nw - (int) nrank * wpc;
+                const uint32_t dst = dp_map(xrow + (nwl * 2 + xb) * 64 + 32 + (lane - HL) * CPL, nrank);
+                const uint32_t bar = dp_map(&hbar[nwl][xb], nrank);
 #pragma unroll
-            for (int g = 0; g < DP_P; g++) {
-                const int x = c0 + 4 * g;
-                if (x >= 0 && x < w) {   // published cells right of the image are already +inf
-                    const int owner = x / xlen;                                   // a float4 never straddles two strips
-                    cur[g] = dp_ld_cluster_v4(dp_map(xr + (x - owner * xlen), (uint32_t) owner));
-                } else {
-                    cur[g] = make_float4(INF, INF, INF, INF);
+                for (int g = 0; g < DP_P; g++) dp_st_async_v4(dst + 16u * g, cur[g], bar);
+            }
+            if (lane >= 32 - 2 * HL && lane < 32 - HL && warp < nwarps - 1) {     // my rightmost 32 published cells
+                const int nw = warp + 1;
+                const uint32_t nrank = (uint32_t) (nw / wpc);
+                const int nwl = nw - (int) nrank * wpc;
+                const uint32_t dst = dp_map(xrow + (nwl * 2 + xb) * 64 + (lane - (32 - 2 * HL)) * CPL, nrank);
+                const uint32_t bar = dp_map(&hbar[nwl][xb], nrank);
+#pragma unroll
+                for (int g = 0; g < DP_P; g++) dp_st_async_v4(dst + 16u * g, cur[g], bar);
+            }
+            dp_mbar_wait(my_bar, (uint32_t) ((hround >> 1) & 1));
+            hround++;
+            if (!central) {
+                const float* hp = halo + (lane < HL ? lane * CPL : 32 + (lane - (32 - HL)) * CPL);
+#pragma unroll
+                for (int g = 0; g < DP_P; g++) {
+                    const int x = c0 + 4 * g;
+                    if (x >= 0 && x < w) cur[g] = *reinterpret_cast<const float4*>(hp + 4 * g);   // cells right of the image arrive as +inf
+                    else cur[g] = make_float4(INF, INF, INF, INF);
                 }
             }
             xb ^= 1;
@@ -932,6 +971,52 @@ __global__ void __launch_bounds__(256) dctc_paint_seams_kernel(uint8_t* __restri
     if (channels > 2) p[2] = 0;
 }
 
+// ---- seam enlarging (lqr_carver_resize to a larger size, src/render.c:357-363,377) ----------------------------------
+// liblqr's lqr_carver_inflate [from memory: PARITY UNPINNED]: every pixel the first n seams went through is doubled;
+// the new pixel sits on its left and holds the integer mean (a + b) / 2 of the pixel and its left neighbour in the
+// original row (a copy in column 0).  One CTA per row: block-wide prefix sum of the "seam pixel" flags gives every
+// original pixel its output column.
+__global__ void __launch_bounds__(256) dctc_inflate_rows_kernel(const uint8_t* __restrict__ orig, size_t pitch, int channels, int w0,
+                                                                const int* __restrict__ vs, int n, uint8_t* __restrict__ out, size_t out_pitch)
+{
+    __shared__ int wsum[8];
+    __shared__ int running;
+    const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint8_t* src = orig + (size_t) y * pitch;
+    uint8_t* dst = out + (size_t) y * out_pitch;
+    const int* vrow = vs + (size_t) y * w0;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < w0; base += 256) {
+        const int x = base + tid;
+        const int v = x < w0 ? vrow[x] : 0;
+        const int flag = (v > 0 && v <= n) ? 1 : 0;
+        int inc = flag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        int before = running;
+        for (int k = 0; k < wid; k++) before += wsum[k];
+        const int pos = x + before + inc - flag;          // output column of the (possibly inserted) first pixel
+        if (x < w0) {
+            const uint8_t* p = src + (size_t) x * channels;
+            uint8_t* q = dst + (size_t) pos * channels;
+            if (flag) {
+                for (int c = 0; c < channels; c++) q[c] = x > 0 ? (uint8_t) (((int) p[c - channels] + (int) p[c]) / 2) : p[c];
+                q += channels;
+            }
+            for (int c = 0; c < channels; c++) q[c] = p[c];
+        }
+        __syncthreads();
+        if (tid == 255) running = before + inc;
+        __syncthreads();
+    }
+}
+
 void dctc_carver_release(dctc_context* ctx)
 {
     if (ctx->c_img) cudaFree(ctx->c_img);
@@ -946,7 +1031,7 @@ void dctc_carver_release(dctc_context* ctx)
     if (ctx->c_band_vals) cudaFree(ctx->c_band_vals);
     if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
     if (ctx->h_band) cudaFreeHost(ctx->h_band);
-    ctx->c_img = nullptr; ctx->c_en = nullptr; ctx->c_m = nullptr; ctx->c_dir = nullptr; ctx->c_seam_log = nullptr; ctx->c_seam_log_cap = 0; ctx->c_raw = nullptr; ctx->c_vs = nullptr; ctx->c_vs_depth = 0; ctx->c_seam = nullptr; ctx->c_band = nullptr;
+    ctx->c_img = nullptr; ctx->c_en = nullptr; ctx->c_m = nullptr; ctx->c_dir = nullptr; ctx->c_seam_log = nullptr; ctx->c_seam_log_cap = 0; ctx->c_raw = nullptr; ctx->c_vs = nullptr; ctx->c_vs_depth = 0; ctx->c_vs_w = 0; ctx->c_seam = nullptr; ctx->c_band = nullptr;
     ctx->c_band_vals = nullptr; ctx->h_mirror = nullptr; ctx->h_band = nullptr;
     ctx->c_w0 = ctx->c_w = ctx->c_h = ctx->c_ch = 0;
     ctx->c_m_valid = false;
@@ -994,6 +1079,7 @@ int dctc_carver_params_changed(dctc_context* ctx)
 
 static int carver_load_impl(dctc_context* ctx, const uint8_t* img, int w, int h, int channels, size_t pitch)
 {
+    // img may be host or device memory (cudaMemcpyDefault: the enlarge path reloads the session from a device buffer)
     ctx->c_w0 = ctx->c_w = w; ctx->c_h = h; ctx->c_ch = channels;
     ctx->c_pitch = ((size_t) w * channels + 15) & ~(size_t) 15;
     const size_t npx = (size_t) w * h;
@@ -1005,7 +1091,7 @@ static int carver_load_impl(dctc_context* ctx, const uint8_t* img, int w, int h,
     CK(ctx, cudaMalloc((void**) &ctx->c_band_vals, sizeof(float) * (size_t) h * 32));
     CK(ctx, cudaMallocHost((void**) &ctx->h_mirror, sizeof(float) * npx));
     CK(ctx, cudaMallocHost((void**) &ctx->h_band, sizeof(float) * (size_t) h * 32 + sizeof(int) * h));
-    CK(ctx, cudaMemcpy2DAsync(ctx->c_img, ctx->c_pitch, img, pitch, (size_t) w * channels, h, cudaMemcpyHostToDevice,
+    CK(ctx, cudaMemcpy2DAsync(ctx->c_img, ctx->c_pitch, img, pitch, (size_t) w * channels, h, cudaMemcpyDefault,
                               ctx->stream));
     int rc = carver_full_energy(ctx);
     if (rc) return rc;
@@ -1119,6 +1205,7 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         CK(ctx, cudaGetLastError());
         ctx->launches++;
         ctx->c_vs_depth = 0;
+        ctx->c_vs_w = ctx->c_w0;
     }
     // cumulative-map plane, rows padded so that the back-track windows (DP_WIN floats) stay inside
     const size_t m_pitch = ctx->c_en_pitch < (size_t) DP_WIN ? (size_t) DP_WIN : ctx->c_en_pitch;
@@ -1227,7 +1314,7 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }
 #endif
         if (ctx->c_dump_vmaps) {   // update_vsmap
-            dctc_vs_update_kernel<<<h, 256, 0, ctx->stream>>>(ctx->c_raw, ctx->c_vs, ctx->c_w0, ctx->c_seam, w_old, ++ctx->c_vs_depth);
+            dctc_vs_update_kernel<<<h, 256, 0, ctx->stream>>>(ctx->c_raw, ctx->c_vs, ctx->c_vs_w, ctx->c_seam, w_old, ++ctx->c_vs_depth);
             ctx->launches++;
         }
         // carve: compact image and energy rows over the seam
@@ -1255,6 +1342,54 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         CK(ctx, cudaMemcpyAsync(seams_out, ctx->c_seam_log, sizeof(int) * (size_t) n_seams * h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return DCTC_OK;
+}
+
+// lqr_carver_resize to a LARGER width (seams_number > 0, src/render.c:357-363): the n seams a shrink would remove,
+// then the inflate kernel; the session continues on the enlarged image (energy map rebuilt), the visibility map of the
+// start frame stays readable through dctc_carver_vmap.
+int dctc_carver_enlarge_width(dctc_context* ctx, int n_seams, int* seams_out)
+{
+    if (!ctx || n_seams < 0) return DCTC_ERR_INVALID;
+    if (!ctx->c_img) return DCTC_ERR_STATE;
+    if (n_seams == 0) return DCTC_OK;
+    if (n_seams >= ctx->c_w || ctx->c_w != ctx->c_w0) return DCTC_ERR_STATE;   // enlarge starts from a freshly loaded frame
+    const int w0 = ctx->c_w, h = ctx->c_h, ch = ctx->c_ch, w1 = w0 + n_seams;
+    CK(ctx, cudaSetDevice(ctx->device));
+    uint8_t* d_orig = nullptr;
+    uint8_t* d_new = nullptr;
+    const size_t p0 = ctx->c_pitch, p1 = ((size_t) w1 * ch + 15) & ~(size_t) 15;
+    CK(ctx, cudaMalloc((void**) &d_orig, p0 * h));
+    cudaError_t e = cudaMalloc((void**) &d_new, p1 * h);
+    if (e != cudaSuccess) { cudaFree(d_orig); return dctc_fail_cuda(ctx, e); }
+    e = cudaMemcpyAsync(d_orig, ctx->c_img, p0 * h, cudaMemcpyDeviceToDevice, ctx->stream);
+    int rc = e == cudaSuccess ? DCTC_OK : dctc_fail_cuda(ctx, e);
+    const bool dump_saved = ctx->c_dump_vmaps;
+    if (rc == DCTC_OK) {
+        ctx->c_dump_vmaps = true;                      // the seams' order per original pixel drives the pixel synthesis
+        rc = dctc_carver_resize_width(ctx, n_seams, seams_out);
+        ctx->c_dump_vmaps = dump_saved;
+    }
+    if (rc == DCTC_OK) {
+        dctc_inflate_rows_kernel<<<h, 256, 0, ctx->stream>>>(d_orig, p0, ch, w0, ctx->c_vs, n_seams, d_new, p1);
+        e = cudaGetLastError();
+        ctx->launches++;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = dctc_fail_cuda(ctx, e);
+    }
+    if (rc == DCTC_OK) {
+        // continue the session on the enlarged image; keep the visibility map of the start frame
+        int* vs = ctx->c_vs;
+        const int depth = ctx->c_vs_depth, vs_w = ctx->c_vs_w;
+        ctx->c_vs = nullptr;
+        dctc_carver_release(ctx);
+        rc = carver_load_impl(ctx, d_new, w1, h, ch, p1);
+        if (rc != DCTC_OK) dctc_carver_release(ctx);
+        if (rc == DCTC_OK) { ctx->c_vs = vs; ctx->c_vs_depth = depth; ctx->c_vs_w = vs_w; }
+        else cudaFree(vs);
+    }
+    cudaFree(d_orig);
+    cudaFree(d_new);
+    return rc;
 }
 
 int dctc_carver_set_incremental(dctc_context* ctx, int on)
@@ -1291,7 +1426,7 @@ int dctc_carver_vmap(dctc_context* ctx, int* vmap_out, int* depth_out)
     if (!ctx->c_img || !ctx->c_vs) return DCTC_ERR_STATE;
     CK(ctx, cudaSetDevice(ctx->device));
     if (vmap_out)
-        CK(ctx, cudaMemcpyAsync(vmap_out, ctx->c_vs, sizeof(int) * (size_t) ctx->c_w0 * ctx->c_h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(vmap_out, ctx->c_vs, sizeof(int) * (size_t) ctx->c_vs_w * ctx->c_h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (depth_out) *depth_out = ctx->c_vs_depth;
     return DCTC_OK;
@@ -1301,7 +1436,7 @@ int dctc_carver_paint_seams(dctc_context* ctx, uint8_t* img, int channels, size_
 {
     if (!ctx || !img || channels < 1 || channels > 4) return DCTC_ERR_INVALID;
     if (!ctx->c_img || !ctx->c_vs || ctx->c_vs_depth <= 0) return DCTC_ERR_STATE;
-    const int w = ctx->c_w0, h = ctx->c_h;
+    const int w = ctx->c_vs_w, h = ctx->c_h;
     if (pitch < (size_t) w * channels) return DCTC_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
     uint8_t* d = nullptr;

@@ -50,6 +50,7 @@ struct dctc_context {
     int* c_raw = nullptr;
     int* c_vs = nullptr;
     int c_vs_depth = 0;
+    int c_vs_w = 0;                // width of the frame the visibility map belongs to (the session's width when it was requested)
     bool c_dump_vmaps = false;
     int* c_seam = nullptr;         // h entries
     int* c_band = nullptr;         // c_band[0]: 'rebuild the cumulative map from scratch' flag of the incremental seam DP; c_band[4]: last-row column of the current seam (device)

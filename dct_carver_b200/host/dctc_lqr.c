@@ -392,22 +392,108 @@ static int transpose(DctcLqrCarver *r)
     return DCTC_LQR_OK;
 }
 
-/* lqr_carver_resize: width first, then height (through a transposed frame) [liblqr, from memory].
- * Enlarging (duplicating seams) is outside the energy hot path and not provided. */
+/* Enlarging by k < w columns [liblqr lqr_carver_inflate, from memory: PARITY UNPINNED]: the k seams a shrink by k would
+ * remove are computed (same energies, same order, recorded in the visibility map), then every pixel of those seams is
+ * doubled: a new pixel is inserted on its left whose channels are the integer mean (a + b) / 2 of the pixel and its
+ * left neighbour in the ORIGINAL row (a copy of the pixel in column 0).  The visibility map of the start frame and the
+ * seam list are kept as for a shrink. */
+static int enlarge_vertical(DctcLqrCarver *r, int k, int record_vs)
+{
+    const int w0 = r->w, h = r->h, ch = r->ch;
+    uint8_t *orig, *out;
+    int x, y, c, rc;
+    (void) record_vs;
+    if (k <= 0) return DCTC_LQR_OK;
+    if (k >= w0) return DCTC_LQR_ERROR;
+    orig = (uint8_t *) malloc((size_t) w0 * h * ch);
+    if (!orig) return DCTC_LQR_NOMEM;
+    for (y = 0; y < h; y++) memcpy(orig + (size_t) y * w0 * ch, r->rgb + (size_t) y * r->pitch * ch, (size_t) w0 * ch);
+    if (r->gpu && g_device_seam_loop && r->delta_x == 1 && r->rigidity == 0.0f) {
+        /* seams, visibility map and the pixel synthesis on the device */
+        int *ns;
+        if (r->seam_len != h) { r->n_seams = 0; r->seam_len = h; }
+        ns = (int *) realloc(r->seams, sizeof(int) * (size_t) (r->n_seams + k) * h);
+        if (!ns) { free(orig); return DCTC_LQR_NOMEM; }
+        r->seams = ns; r->seams_cap = r->n_seams + k;
+        rc = dctc_carver_load(r->gpu, orig, w0, h, ch, (size_t) w0 * ch);
+        if (rc == DCTC_OK) rc = dctc_carver_enlarge_width(r->gpu, k, r->seams + (size_t) r->n_seams * h);
+        if (rc == DCTC_OK) {
+            out = (uint8_t *) malloc((size_t) (w0 + k) * h * ch);
+            free(r->vs);
+            r->vs = (int *) calloc((size_t) w0 * h, sizeof(int));
+            if (!out || !r->vs) { free(out); free(orig); return DCTC_LQR_NOMEM; }
+            r->vs_w = w0; r->vs_h = h;
+            if (dctc_carver_vmap(r->gpu, r->vs, &r->vs_depth) != DCTC_OK || dctc_carver_image(r->gpu, out) != DCTC_OK) {
+                free(out); free(orig);
+                return DCTC_LQR_ERROR;
+            }
+            dctc_carver_set_dump_vmaps(r->gpu, 0);
+            r->n_seams += k;
+            free(r->rgb); free(orig);
+            r->rgb = out; r->w = r->pitch = w0 + k;
+            return DCTC_LQR_OK;
+        }
+        dctc_carver_set_dump_vmaps(r->gpu, 0);
+        if (rc != DCTC_ERR_UNSUPPORTED) { free(orig); return DCTC_LQR_ERROR; }
+        /* wider than the device seam kernel covers: host loop below */
+    }
+    rc = carve_vertical(r, k, 1);                      /* the seams: r->vs holds their order over the start frame */
+    if (rc) { free(orig); return rc; }
+    out = (uint8_t *) malloc((size_t) (w0 + k) * h * ch);
+    if (!out) { free(orig); return DCTC_LQR_NOMEM; }
+    for (y = 0; y < h; y++) {
+        const uint8_t *src = orig + (size_t) y * w0 * ch;
+        uint8_t *dst = out + (size_t) y * (w0 + k) * ch;
+        int n = 0;
+        for (x = 0; x < w0; x++) {
+            const int vis = r->vs[(size_t) y * w0 + x];
+            if (vis > 0 && vis <= k) {
+                for (c = 0; c < ch; c++)
+                    dst[(size_t) (x + n) * ch + c] = x > 0 ? (uint8_t) (((int) src[(size_t) (x - 1) * ch + c] + (int) src[(size_t) x * ch + c]) / 2)
+                                                           : src[(size_t) x * ch + c];
+                n++;
+            }
+            memcpy(dst + (size_t) (x + n) * ch, src + (size_t) x * ch, ch);
+        }
+    }
+    free(r->rgb); free(orig);
+    r->rgb = out; r->w = r->pitch = w0 + k;
+    return DCTC_LQR_OK;
+}
+
+/* one axis of lqr_carver_resize: shrink, or enlarge in passes of fewer than w columns each */
+static int resize_axis(DctcLqrCarver *r, int w1, int *first)
+{
+    int rc;
+    if (w1 < r->w) {
+        rc = carve_vertical(r, r->w - w1, *first);
+        if (rc) return rc;
+        *first = 0;
+    }
+    while (w1 > r->w) {
+        const int k = w1 - r->w < r->w - 1 ? w1 - r->w : r->w - 1;
+        if (k <= 0) return DCTC_LQR_ERROR;
+        rc = enlarge_vertical(r, k, *first);
+        if (rc) return rc;
+        *first = 0;
+    }
+    return DCTC_LQR_OK;
+}
+
+/* lqr_carver_resize: width first, then height (through a transposed frame) [liblqr, from memory]. */
 int dctc_lqr_carver_resize(DctcLqrCarver *r, int w1, int h1)
 {
-    int rc, first = r->dump_vmaps;
+    int rc, first;
     if (!r || w1 <= 0 || h1 <= 0) return DCTC_LQR_ERROR;
-    if (w1 > dctc_lqr_carver_get_width(r) || h1 > dctc_lqr_carver_get_height(r)) return DCTC_LQR_ERROR;
-    if (w1 < r->w) {
-        rc = carve_vertical(r, r->w - w1, first);
+    first = r->dump_vmaps;
+    if (w1 != r->w) {
+        rc = resize_axis(r, w1, &first);
         if (rc) return rc;
-        first = 0;
     }
-    if (h1 < r->h) {
+    if (h1 != r->h) {
         rc = transpose(r);
         if (rc) return rc;
-        rc = carve_vertical(r, r->w - h1, first);
+        rc = resize_axis(r, h1, &first);
         if (rc) { transpose(r); return rc; }
         rc = transpose(r);
         if (rc) return rc;
@@ -512,8 +598,8 @@ int dctc_render(const uint8_t *img, int w, int h, int channels, const DctcPlugIn
     /* render, src/render.c:357-377 */
     if (vals->vertically) { new_w = w; new_h = h + vals->seams_number; }
     else { new_w = w + vals->seams_number; new_h = h; }
-    rc = DCTC_ERR_UNSUPPORTED;
-    if (new_w > w || new_h > h || new_w <= 0 || new_h <= 0) goto out;
+    rc = DCTC_ERR_INVALID;
+    if (new_w <= 0 || new_h <= 0) goto out;          /* seams_number > 0 enlarges (src/render.c:357-363) */
     if (vals->output_energy) {
         res->energy_image = (uint8_t *) malloc((size_t) w * h);
         if (!res->energy_image || dctc_lqr_carver_get_energy_image(carver, res->energy_image)) { rc = DCTC_ERR_CUDA; goto out; }

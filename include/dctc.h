@@ -149,6 +149,13 @@ int dctc_carver_image(dctc_context *ctx, uint8_t *out);
  * at the time of removal.  Mirrors lqr_carver_resize(carver, w - n_seams, h) (src/render.c:377) with
  * delta_x = 1, rigidity = 0 (src/render.c:313). */
 int dctc_carver_resize_width(dctc_context *ctx, int n_seams, int *seams_out);
+/* Enlarging: lqr_carver_resize(carver, w + n_seams, h) as the plug-in calls it for seams_number > 0
+ * (src/render.c:357-363,377).  The n_seams seams a shrink would remove are computed on a freshly loaded session (same
+ * energies, same order; seams_out as above), then every pixel of those seams is doubled on the device: the new pixel
+ * sits on its left with the integer mean (a + b) / 2 of the pixel and its left neighbour in the original row (a copy in
+ * column 0) [liblqr lqr_carver_inflate, from memory: parity unpinned].  The session continues on the enlarged image
+ * (dctc_carver_image / _energy / _width reflect it); dctc_carver_vmap returns the start frame's visibility map. */
+int dctc_carver_enlarge_width(dctc_context *ctx, int n_seams, int *seams_out);
 /* Optional: let the device loop update its cumulative map incrementally after each seam, like liblqr's update_mmap
  * (only the cells the removed seam can have changed are recomputed; a row whose changed range gets too wide falls
  * back to the full rebuild).  Same seams bit for bit; off by default because the full rebuild on an 8-CTA cluster is

@@ -70,13 +70,52 @@ def test_height_retarget_is_width_retarget_of_the_transpose():
     assert np.array_equal(a["image"], bres["image"].transpose(1, 0, 2))
 
 
-def test_render_refuses_without_gpu_or_callback_and_enlarging():
+def test_render_refuses_without_gpu_or_callback():
     import dct_carver_b200 as dc
     img = ol.synth_image(20, 20, 3, 1, 0)
     with pytest.raises(dc.DctcError) as e:
         host.render(img, -2)
     assert e.value.status == dc.ERR_NO_DEVICE        # no CPU fallback
+
+
+def inflate_from_vmap(img, vmap, k):
+    """liblqr's lqr_carver_inflate restated in numpy [from memory: parity unpinned]: every pixel of the first k seams is
+    doubled, the new pixel on its left = integer mean of the pixel and its left neighbour (a copy in column 0)."""
+    h, w, ch = img.shape
+    out = np.zeros((h, w + k, ch), np.uint8)
+    for y in range(h):
+        n = 0
+        for x in range(w):
+            if 0 < vmap[y, x] <= k:
+                out[y, x + n] = ((img[y, x - 1].astype(int) + img[y, x].astype(int)) // 2) if x > 0 else img[y, x]
+                n += 1
+            out[y, x + n] = img[y, x]
+        assert n == k
+    return out
+
+
+@pytest.mark.parametrize("vertically", [False, True])
+def test_enlarging_duplicates_the_seams_a_shrink_would_remove(vertically):
+    """seams_number > 0 (src/render.c:357-363): same seams, same order as the shrink by the same amount; pixel synthesis
+    by duplicate-and-average."""
+    img = ol.synth_image(41, 37, 3, 77, 0)
+    k = 7
     cbp, ep = ref_callback(8, 0.5, 0.5)
-    with pytest.raises(dc.DctcError) as e:
-        host.render(img, +2, callback=cbp, callback_extra=C.byref(ep))
-    assert e.value.status == dc.ERR_UNSUPPORTED
+    grow = host.render(img, +k, 8, vertically=vertically, callback=cbp, callback_extra=C.byref(ep))
+    shrink = host.render(img, -k, 8, vertically=vertically, callback=cbp, callback_extra=C.byref(ep))
+    assert np.array_equal(grow["seams"], shrink["seams"])
+    assert np.array_equal(grow["vmap"], shrink["vmap"]) and grow["vmap_depth"] == k
+    if vertically:
+        want = inflate_from_vmap(np.ascontiguousarray(img.transpose(1, 0, 2)), grow["vmap"], k).transpose(1, 0, 2)
+        assert grow["image"].shape == (37 + k, 41, 3)
+    else:
+        want = inflate_from_vmap(img, grow["vmap"], k)
+        assert grow["image"].shape == (37, 41 + k, 3)
+    assert np.array_equal(grow["image"], want)
+
+
+def test_enlarging_beyond_twice_the_width_runs_in_passes():
+    img = ol.synth_image(12, 9, 1, 5, 0)
+    cbp, ep = ref_callback(4, 0.5, 0.5)
+    got = host.render(img, +15, 4, callback=cbp, callback_extra=C.byref(ep))    # 12 -> 23 (+11), then 23 -> 27 (+4)
+    assert got["image"].shape == (9, 27, 1)

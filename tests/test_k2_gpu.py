@@ -381,3 +381,46 @@ def test_device_vmap_and_seam_display_equal_host_carver(ctx, ch, w, h, n):
     if ch > 2:
         ref[ys, xs, 2] = 0
     assert np.array_equal(painted, ref)
+
+
+@pytest.mark.parametrize("ch,w,h,k", [(3, 150, 90, 25), (1, 97, 40, 30), (4, 64, 33, 9), (3, 1930, 64, 12)])
+def test_device_seam_enlarging_equals_host_carver(ctx, ch, w, h, k):
+    """seams_number > 0 (src/render.c:357-363; lqr_carver_resize to a larger size): the device path (seam loop + inflate
+    kernel) gives the image of the host carver's enlarge (host seam loop) and of the numpy restatement of
+    lqr_carver_inflate applied to the device's visibility map [pixel synthesis from memory: parity unpinned]; the
+    seams are those of the shrink by the same amount; the session continues on the enlarged image."""
+    from dct_carver_b200 import host
+    from test_carver_cpu import inflate_from_vmap
+    img = ol.synth_image(w, h, ch, 1234 + w, 0)
+    ctx.set_params(8, 0.5, 0.5)
+    want = host.render(img, +k, 8, 0.5, 0.5, ctx=ctx, device_loop=False)
+    got = host.render(img, +k, 8, 0.5, 0.5, ctx=ctx, device_loop=True)
+    assert got["image"].shape == (h, w + k, ch)
+    assert np.array_equal(got["seams"], want["seams"])
+    assert np.array_equal(got["vmap"], want["vmap"]) and got["vmap_depth"] == k
+    assert np.array_equal(got["image"], want["image"])
+    assert np.array_equal(got["image"], inflate_from_vmap(img.reshape(h, w, ch), got["vmap"], k))
+    # straight through the C ABI: seams of the shrink, session continues on the enlarged frame with a fresh energy map
+    ctx.carver_load(img)
+    shrink = ctx.carver_resize_width(k)
+    ctx.carver_load(img)
+    seams = ctx.carver_enlarge_width(k)
+    assert np.array_equal(seams, shrink)
+    assert ctx.carver_size() == (w + k, h)
+    assert np.array_equal(ctx.carver_image(), got["image"])
+    assert np.array_equal(ctx.carver_energy(), ctx.energy_full(got["image"]))
+    vmap, depth = ctx.carver_vmap(w, h)
+    assert depth == k and np.array_equal(vmap, got["vmap"])
+
+
+def test_device_seam_enlarging_state_errors(ctx):
+    img = ol.synth_image(16, 8, 3, 3, 0)
+    ctx.set_params(8, 0.5, 0.5)
+    ctx.carver_load(img)
+    with pytest.raises(dc.DctcError) as e:
+        ctx.carver_enlarge_width(16)              # at most w - 1 seams per pass
+    assert e.value.status == dc.ERR_STATE
+    ctx.carver_resize_width(2)
+    with pytest.raises(dc.DctcError) as e:
+        ctx.carver_enlarge_width(3)               # needs a freshly loaded frame
+    assert e.value.status == dc.ERR_STATE
