@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdctc.so")
+LIB_PATH = os.environ.get("DCTC_LIB") or os.path.join(_HERE, "libdctc.so")   # DCTC_LIB: experimental builds (tools/build_exp.sh)
 
 OK = 0
 ERR_INVALID, ERR_BLOCKSIZE, ERR_NOMEM, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7

@@ -75,6 +75,7 @@ int dctc_create(dctc_context** out, int device)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc((void**) &ctx->tc_counters, DCTC_TC_COUNTERS * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->tc_counters, 0, DCTC_TC_COUNTERS * sizeof(int));   // the tensor-core kernel leaves its counter at 0
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t1);
     for (int i = 0; i < DCTC_SLOTS && e == cudaSuccess; i++) {

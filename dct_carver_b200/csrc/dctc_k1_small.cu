@@ -3,15 +3,16 @@
 // (SURVEY 8d): the kernel is organised around keeping the image rows in flight, not around the arithmetic.
 //
 // Same operator as dctc_k1_tile.cu (reference chain src/render.c:134-157 -> dctNxN src/dct.c:77-94 -> ddct2d,
-// src/fft2d/fftsg2d.c:566-627, unnormalised -> weighted_max_dct_correlation src/dct.c:96-110) and the SAME FP32
-// operation order (luma fmaf chain, dctc_dct_fwd<B> along x, the packed twin of dctc_dct_fwd<B> along y, last-arg-max
-// fold), so its maps are bit-identical to the tile kernel's and the two can be mixed (band updates of a carver
-// session run in the tile kernel).
+// src/fft2d/fftsg2d.c:566-627, unnormalised -> weighted_max_dct_correlation src/dct.c:96-110) with the same transform
+// code (dctc_dct_fwd<B> along x, its packed twin along y, last-arg-max fold).  RGB luma is the EXACT integer
+// 2126 R + 7152 G + 722 B (two dp2a per pixel instead of three byte->float conversions and an FMA chain; the factor
+// 1/10000 folds into the final weight), so RGB maps agree with the tile kernel within the stated tolerance, grey maps
+// bit for bit.  Carver sessions never mix the two (they pin the FP32 tile / march kernels).
 //
 //   * a CTA owns a strip of 128 columns and marches down SEG rows; thread t owns column x0+t
 //   * raw interleaved rows are copied global -> shared with 16-byte cp.async, 8 rows per chunk, two chunks ahead
-//   * conversion: 4 pixels per task from three 32-bit shared loads (PRMT + FADD byte -> float, exact), luma rows
-//     double buffered in shared memory
+//   * conversion: 4 pixels per task from three 32-bit shared loads (two PRMT, one shift, eight dp2a, four I2F), the
+//     tasks cover the halo columns too (34 quads per row); luma rows double buffered in shared memory
 //   * per new image row ONE DCT-B along x per thread; the B coefficients of the last B rows live in a register
 //     ring packed as k1 pairs (float2), the y-pass is B/2 packed DCT-B straight from registers, then the fold and
 //     one coalesced float store per pixel
@@ -26,7 +27,7 @@ constexpr int LWP = MW + 8;    // staged luma row: index i <-> column x0 - 4 + i
 template <int CH, int B>
 struct RawGeom {
     static constexpr int R1 = B / 2;                                    // samples after the pixel
-    static constexpr int CHUNKS = (16 + (MW + R1) * CH + 15) / 16;      // 16-byte chunks per staged raw row
+    static constexpr int CHUNKS = (16 + (MW + 4) * CH + 15) / 16;       // 16-byte chunks per staged raw row (quads up to x0+131)
     static constexpr int ROW = CHUNKS * 16;
     static constexpr int PER = (8 * CHUNKS + MW - 1) / MW;              // chunks per thread and row block
 };
@@ -166,21 +167,25 @@ struct StageMap {
     }
 };
 
+// RGB luma as the exact integer 2126 R + 7152 G + 722 B (< 2^22: exact as a float); grey stays the byte itself
+constexpr float LUMA_INT_SCALE = 1.0f / 10000.0f;
+constexpr uint32_t LUMA_RG = (7152u << 16) | 2126u;    // dp2a.lo: R * 2126 + G * 7152 from bytes 0, 1
+constexpr uint32_t LUMA_B = 722u;                       // dp2a.hi: B * 722 (+ 0 * byte 3) from bytes 2, 3
+
 template <int CH>
 __device__ __forceinline__ float luma_raw(const uint8_t* __restrict__ p)
 {
-    if (CH == 3) return fmaf(0.2126f, (float) p[0], fmaf(0.7152f, (float) p[1], 0.0722f * (float) p[2]));
+    if (CH == 3) return (float) (2126u * p[0] + 7152u * p[1] + 722u * p[2]);
     return (float) p[0];
 }
 
-// byte k (0..3 of w0, 4..7 of w1) -> float, exactly: the byte becomes the low mantissa bits of 2^23 + byte
-__device__ __forceinline__ float byte_to_float(uint32_t w0, uint32_t w1, int k)
+// byte k (0..3) of w -> float, exactly: the byte becomes the low mantissa bits of 2^23 + byte
+__device__ __forceinline__ float byte_to_float(uint32_t w, int k)
 {
-    const uint32_t src = k < 4 ? w0 : w1;
-    return __uint_as_float(__byte_perm(src, 0x4B000000u, 0x7540u | (uint32_t) (k & 3))) - 8388608.0f;
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t) k)) - 8388608.0f;
 }
 
-// luma of four consecutive pixels from their CH*4 raw bytes (4-byte aligned); same arithmetic as dctc_luma255
+// luma of four consecutive pixels from their CH*4 raw bytes (4-byte aligned); same values as luma_raw
 template <int CH>
 __device__ __forceinline__ float4 quad_luma(const uint8_t* __restrict__ p)
 {
@@ -188,53 +193,67 @@ __device__ __forceinline__ float4 quad_luma(const uint8_t* __restrict__ p)
     float4 l;
     if (CH == 3) {
         const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-        l.x = fmaf(0.2126f, byte_to_float(w0, w1, 0), fmaf(0.7152f, byte_to_float(w0, w1, 1), 0.0722f * byte_to_float(w0, w1, 2)));
-        l.y = fmaf(0.2126f, byte_to_float(w0, w1, 3), fmaf(0.7152f, byte_to_float(w0, w1, 4), 0.0722f * byte_to_float(w0, w1, 5)));
-        l.z = fmaf(0.2126f, byte_to_float(w1, w2, 2), fmaf(0.7152f, byte_to_float(w1, w2, 3), 0.0722f * byte_to_float(w1, w2, 4)));
-        l.w = fmaf(0.2126f, byte_to_float(w1, w2, 5), fmaf(0.7152f, byte_to_float(w1, w2, 6), 0.0722f * byte_to_float(w1, w2, 7)));
+        const uint32_t p1 = __byte_perm(w0, w1, 0x6543), p2 = __byte_perm(w1, w2, 0x5432), p3 = w2 >> 8;
+        l.x = (float) __dp2a_lo(LUMA_RG, w0, __dp2a_hi(LUMA_B, w0, 0u));
+        l.y = (float) __dp2a_lo(LUMA_RG, p1, __dp2a_hi(LUMA_B, p1, 0u));
+        l.z = (float) __dp2a_lo(LUMA_RG, p2, __dp2a_hi(LUMA_B, p2, 0u));
+        l.w = (float) __dp2a_lo(LUMA_RG, p3, __dp2a_hi(LUMA_B, p3, 0u));
     } else {
         const uint32_t w0 = w[0];
-        l.x = byte_to_float(w0, w0, 0);
-        l.y = byte_to_float(w0, w0, 1);
-        l.z = byte_to_float(w0, w0, 2);
-        l.w = byte_to_float(w0, w0, 3);
+        l.x = byte_to_float(w0, 0);
+        l.y = byte_to_float(w0, 1);
+        l.z = byte_to_float(w0, 2);
+        l.w = byte_to_float(w0, 3);
     }
     return l;
 }
 
-// 8 raw rows -> 8 luma rows; staged index i <-> image column clamp(x0 - 4 + i) (src/render.c:122-132).
-// Thread t converts quad t%32 (columns x0+4q .. x0+4q+3) of rows t/32 and t/32+4; the R0 columns left of the strip
-// and the R1 columns right of it are single-pixel tasks of the first threads.
-template <int CH, int B, int NROWS = 8>
-__device__ __forceinline__ void convert_raw(const DctcK1Args& a, const uint8_t* __restrict__ R, float* __restrict__ L, int x0, int tid)
-{
+// NROWS raw rows -> luma rows; staged index i <-> image column clamp(x0 - 4 + i) (src/render.c:122-132).
+// A task is one 4-pixel group of one row: 34 quads per row cover the columns x0-4 .. x0+131, i.e. the strip and its
+// halo columns; a thread owns the same tasks for every chunk of a segment, so their offsets and the border test are
+// computed once (ConvMap).  Quads that touch the image border take the per-pixel clamped path.
+constexpr int NQUAD = LWP / 4;
+template <int CH, int B>
+struct ConvMap {
     using G = RawGeom<CH, B>;
-    constexpr int R0 = B / 2 - 1, R1 = B / 2;
-    const int q = tid & 31, gx = x0 + 4 * q;
-    const bool inside = gx + 3 < a.w;
+    static constexpr int PER = (8 * NQUAD + MW - 1) / MW;   // 3
+    int roff[PER];     // byte offset of the task's raw quad inside a raw buffer, -1: no task; bit 30 set: the quad
+                       // touches the image border (per-pixel clamped path)
+    int loff[PER];     // float index inside a luma buffer
+    static constexpr int BORDER = 1 << 30;
+    __device__ __forceinline__ void init(const DctcK1Args& a, int x0, int tid)
+    {
 #pragma unroll
-    for (int i = 0; i < (NROWS > 4 ? 2 : 1); i++) {
-        const int ly = (tid >> 5) + 4 * i;
-        if (NROWS < 4 && ly >= NROWS) break;
-        const uint8_t* r = R + ly * G::ROW + 16 + 4 * CH * q;
-        float4 l;
-        if (inside) {
-            l = quad_luma<CH>(r);
-        } else {
-            float t[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) t[k] = luma_raw<CH>(r + (min(gx + k, a.w - 1) - gx) * CH);
-            l = make_float4(t[0], t[1], t[2], t[3]);
+        for (int i = 0; i < PER; i++) {
+            const int task = tid + i * MW;
+            const int r = task / NQUAD, q = task - r * NQUAD - 1;   // row 0..7, quad -1..32
+            const int g = x0 + 4 * q;
+            roff[i] = task < 8 * NQUAD ? (r * G::ROW + 16 + 4 * CH * q) | ((g >= 0 && g + 3 < a.w) ? 0 : BORDER) : -1;
+            loff[i] = r * LWP + 4 * q + 4;
         }
-        *reinterpret_cast<float4*>(L + ly * LWP + 4 + 4 * q) = l;
     }
-    if (tid < NROWS * (R0 + R1)) {
-        const int ly = tid / (R0 + R1), k = tid - ly * (R0 + R1);
-        const int col = k < R0 ? -R0 + k : MW + (k - R0);             // relative to x0
-        const int gxc = max(0, min(x0 + col, a.w - 1));
-        L[ly * LWP + 4 + col] = luma_raw<CH>(R + ly * G::ROW + 16 + (gxc - x0) * CH);
+    template <int NROWS>
+    __device__ __forceinline__ void convert(const DctcK1Args& a, const uint8_t* __restrict__ R, float* __restrict__ L, int x0) const
+    {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int ro = roff[i] & ~BORDER;
+            if (roff[i] < 0 || (NROWS < 8 && ro >= NROWS * G::ROW)) continue;
+            const uint8_t* r = R + ro;
+            float4 l;
+            if (!(roff[i] & BORDER)) {
+                l = quad_luma<CH>(r);
+            } else {
+                const int g = x0 + (loff[i] % LWP) - 4;              // image column of the quad's first pixel
+                float t[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) t[k] = luma_raw<CH>(r + (max(0, min(g + k, a.w - 1)) - g) * CH);
+                l = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            *reinterpret_cast<float4*>(L + loff[i]) = l;
+        }
     }
-}
+};
 
 // ---- march -----------------------------------------------------------------------------------------------------
 template <int B, int SLOT>
@@ -276,12 +295,12 @@ __device__ __forceinline__ float ypass(const float2 (&H2)[B][B / 2], float we, f
 // row RW of the chunk: the new image row lands in ring slot (RW + B - 1) % B, the window of output row gy+RW starts in
 // slot RW % B; `o` points at this thread's pixel of that output row
 template <int B, int RW, bool UNIFORM>
-__device__ __forceinline__ void step(float2 (&H2)[B][B / 2], const float* __restrict__ Lbuf, int tid, const DctcK1Args& a,
+__device__ __forceinline__ void step(float2 (&H2)[B][B / 2], const float* __restrict__ Lbuf, int tid, float we, float wt,
                                      float* __restrict__ o, bool ok)
 {
     xpass<B, (RW + B - 1) % B>(H2, Lbuf + RW * LWP, tid);
-    const float e = ypass<B, RW % B, UNIFORM>(H2, a.w_edges, a.w_textures);
-    if (ok) *o = e;
+    const float e = ypass<B, RW % B, UNIFORM>(H2, we, wt);
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.global.f32 [%0], %1;\n}" ::"l"(o), "f"(e), "r"((int) ok) : "memory");
 }
 
 template <int B, bool UNIFORM, int CH>
@@ -300,6 +319,10 @@ __global__ void __launch_bounds__(MW, B == 2 ? 8 : 6) dctc_k1_small_kernel(const
     const int gx = x0 + tid;
     const bool colok = gx < a.w;
     float2 H2[B][B / 2];
+    const float lscale = CH == 3 ? LUMA_INT_SCALE : 1.0f;       // RGB luma is 10000 x the 0..255 luma
+    const float we = a.w_edges * lscale, wt = a.w_textures * lscale;
+    ConvMap<CH, B> cm;
+    cm.init(a, x0, tid);
 
     // chunk 0 = virtual rows y0-R0 .. (only the first B-1 are used: prologue); chunk c >= 1 = rows y0+R1+8(c-1) .. +7,
     // which feed output rows y0+8(c-1) .. +7.  Raw buffers rotate over three slots (two chunks in flight).
@@ -312,7 +335,7 @@ __global__ void __launch_bounds__(MW, B == 2 ? 8 : 6) dctc_k1_small_kernel(const
     else asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncthreads();
-    convert_raw<CH, B, B - 1>(a, Raw[0], L[0], x0, tid);
+    cm.template convert<B - 1>(a, Raw[0], L[0], x0);
     __syncthreads();
     if (B == 4) {
         xpass<B, 0>(H2, L[0] + 0 * LWP, tid);
@@ -331,29 +354,29 @@ __global__ void __launch_bounds__(MW, B == 2 ? 8 : 6) dctc_k1_small_kernel(const
         if (c + 2 < nchunks) sm.stage(a, img, Raw[fslot], y0 + R1 + 8 * (c + 1), x0);
         else asm volatile("cp.async.commit_group;" ::: "memory");
         float* Lb = L[c & 1];
-        convert_raw<CH, B>(a, Raw[slot], Lb, x0, tid);
+        cm.template convert<8>(a, Raw[slot], Lb, x0);
         __syncthreads();
         // one pointer per chunk, advanced by the pitch: no 64-bit multiply and no divergent guard per pixel
         float* o = out + (size_t) gy * a.out_pitch + gx;
         const size_t op = a.out_pitch;
         if (gy + 8 <= a.h) {
-            step<B, 0, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
-            step<B, 1, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
-            step<B, 2, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
-            step<B, 3, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
-            step<B, 4, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
-            step<B, 5, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
-            step<B, 6, UNIFORM>(H2, Lb, tid, a, o, colok); o += op;
-            step<B, 7, UNIFORM>(H2, Lb, tid, a, o, colok);
+            step<B, 0, UNIFORM>(H2, Lb, tid, we, wt, o, colok); o += op;
+            step<B, 1, UNIFORM>(H2, Lb, tid, we, wt, o, colok); o += op;
+            step<B, 2, UNIFORM>(H2, Lb, tid, we, wt, o, colok); o += op;
+            step<B, 3, UNIFORM>(H2, Lb, tid, we, wt, o, colok); o += op;
+            step<B, 4, UNIFORM>(H2, Lb, tid, we, wt, o, colok); o += op;
+            step<B, 5, UNIFORM>(H2, Lb, tid, we, wt, o, colok); o += op;
+            step<B, 6, UNIFORM>(H2, Lb, tid, we, wt, o, colok); o += op;
+            step<B, 7, UNIFORM>(H2, Lb, tid, we, wt, o, colok);
         } else {
-            step<B, 0, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 0 < a.h); o += op;
-            step<B, 1, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 1 < a.h); o += op;
-            step<B, 2, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 2 < a.h); o += op;
-            step<B, 3, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 3 < a.h); o += op;
-            step<B, 4, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 4 < a.h); o += op;
-            step<B, 5, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 5 < a.h); o += op;
-            step<B, 6, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 6 < a.h); o += op;
-            step<B, 7, UNIFORM>(H2, Lb, tid, a, o, colok && gy + 7 < a.h);
+            step<B, 0, UNIFORM>(H2, Lb, tid, we, wt, o, colok && gy + 0 < a.h); o += op;
+            step<B, 1, UNIFORM>(H2, Lb, tid, we, wt, o, colok && gy + 1 < a.h); o += op;
+            step<B, 2, UNIFORM>(H2, Lb, tid, we, wt, o, colok && gy + 2 < a.h); o += op;
+            step<B, 3, UNIFORM>(H2, Lb, tid, we, wt, o, colok && gy + 3 < a.h); o += op;
+            step<B, 4, UNIFORM>(H2, Lb, tid, we, wt, o, colok && gy + 4 < a.h); o += op;
+            step<B, 5, UNIFORM>(H2, Lb, tid, we, wt, o, colok && gy + 5 < a.h); o += op;
+            step<B, 6, UNIFORM>(H2, Lb, tid, we, wt, o, colok && gy + 6 < a.h); o += op;
+            step<B, 7, UNIFORM>(H2, Lb, tid, we, wt, o, colok && gy + 7 < a.h);
         }
         slot = slot == 2 ? 0 : slot + 1;
     }

@@ -224,8 +224,8 @@ struct StageMap {
 
 
 // Luma in this kernel is the EXACT integer 2126 R + 7152 G + 722 B (= 10000 * 255 * liblqr's LQR_ER_LUMA value, below
-// 2^22, so its float is exact too); grey is 10000 * v.  Two u8 dot products per pixel (coefficients split into a high
-// and a low byte) replace three byte->float conversions and an FMA chain.  The factor 2^-13 of the scaled x-pass
+// 2^22, so its float is exact too); grey is 10000 * v.  Two dp2a per pixel (16-bit coefficients times the pixel's bytes)
+// replace three byte->float conversions and an FMA chain.  The factor 2^-13 of the scaled x-pass
 // (fp16 range of the hi/lo operands) and the 1/10000 are folded into the final weight.
 constexpr float LUMA_WEIGHT_SCALE = 8192.0f / 10000.0f;
 
@@ -243,12 +243,13 @@ __device__ __forceinline__ void quad_luma(const uint8_t* __restrict__ p, float (
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
     if (CH == 3) {
         const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-        constexpr uint32_t CLO = 0x00D2F04Eu, CHI = 0x00021B08u;   // (78, 240, 210, 0), (8, 27, 2, 0): 2126, 7152, 722
-        const uint32_t p1 = __byte_perm(w0, w1, 0x6543), p2 = __byte_perm(w1, w2, 0x5432);
-        l[0] = (float) __dp4a(w0, CLO, __dp4a(w0, CHI, 0u) << 8);
-        l[1] = (float) __dp4a(p1, CLO, __dp4a(p1, CHI, 0u) << 8);
-        l[2] = (float) __dp4a(p2, CLO, __dp4a(p2, CHI, 0u) << 8);
-        l[3] = (float) __dp4a(w2, CLO << 8, __dp4a(w2, CHI << 8, 0u) << 8);
+        // dp2a.lo: R * 2126 + G * 7152 from bytes 0, 1; dp2a.hi: B * 722 (+ 0 * byte 3) from bytes 2, 3
+        constexpr uint32_t CRG = (7152u << 16) | 2126u, CB = 722u;
+        const uint32_t p1 = __byte_perm(w0, w1, 0x6543), p2 = __byte_perm(w1, w2, 0x5432), p3 = w2 >> 8;
+        l[0] = (float) __dp2a_lo(CRG, w0, __dp2a_hi(CB, w0, 0u));
+        l[1] = (float) __dp2a_lo(CRG, p1, __dp2a_hi(CB, p1, 0u));
+        l[2] = (float) __dp2a_lo(CRG, p2, __dp2a_hi(CB, p2, 0u));
+        l[3] = (float) __dp2a_lo(CRG, p3, __dp2a_hi(CB, p3, 0u));
     } else {
         const uint32_t w0 = w[0];
 #pragma unroll
@@ -523,7 +524,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
     // shrinks to 40.
     auto begin_item = [&](bool first) -> int {
         if (tid == 0) {
-            s.work = atomicAdd(counter, 1);
+            // Every CTA fetches until its first item >= n_items: n_items + gridDim.x fetches in all, so the wrapping
+            // increment leaves the counter at 0 for the next launch that uses it (no memset between launches).
+            s.work = (int) atomicInc(reinterpret_cast<unsigned int*>(counter), (unsigned int) n_items + gridDim.x - 1u);
             if (!first) {
                 mbar_inval(smem_u32(&s.bar_a_free));
                 mbar_inval(smem_u32(&s.bar_a_free_lo));
@@ -712,7 +715,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
 
 // Returns cudaErrorNotSupported when the configuration is outside this kernel's fast path (the caller then uses
 // the FP32 march kernel): needs 1 or 3 channels and 16-byte aligned row pointers / pitches.
-// `counter` is a device int owned by the context (work-item counter of the persistent kernel).
+// `counter` is a device int owned by the context (work-item counter of the persistent kernel), zero before the launch;
+// the kernel leaves it at zero again.
 cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, int* counter, int sm_count, cudaStream_t stream)
 {
     if (a.w <= 0 || a.h <= 0 || n_frames <= 0) return cudaSuccess;
@@ -722,18 +726,41 @@ cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, 
                       (!a.top || aligned16(a.top, a.top_pitch)) && (!a.bot || aligned16(a.bot, a.bot_pitch));
     if (!fast || !counter) return cudaErrorNotSupported;
     const int strips = (a.w + MW - 1) / MW;
-    // segment height: long segments amortise the 8-row prologue; keep >= ~6 items per SM so the tail stays short
-    int seg = 256;   // (measured on 16 frames of 4K: 1024/512 rows 50.5 us per frame, 256 rows 49.3, 128 rows 50.5, 64 rows 54.7)
-    // (one 4K frame per launch: 70.9 us with >= 6 items per SM, 80.8 us with >= 8 or 12, 74.7 us with >= 2)
-    while (seg > 32 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 6LL * sm_count) seg >>= 1;
-    int segs = (a.h + seg - 1) / seg;
-    seg = (((a.h + segs - 1) / segs) + 7) & ~7;     // even segments (1080 rows: 5 x 216 instead of 4 x 256 + 56)
-    segs = (a.h + seg - 1) / seg;
+    // Segment height.  An item of S rows costs S/8 + 2 steps (two prologue groups); the 2 x sm_count resident CTAs take
+    // items from a counter, so a launch lasts about ceil(items / CTAs) x (S/8 + 2) steps when the items are few, and
+    // (total steps + 2 x items) / CTAs when they are many.  Candidates: 256 / 128 / 64 / 32 rows (evened out over the
+    // image height) and the "one round" split that gives every CTA at most one item (one 4K frame: 9 segments of 240
+    // rows = 270 items on 296 CTAs, 32 steps, instead of 1020 items of 64 rows, 4 rounds of 10 steps).
+    // (measured on 16 frames of 4K: 1024/512 rows 50.5 us per frame, 256 rows 49.3, 128 rows 50.5, 64 rows 54.7)
+    const long long ctas = 2LL * sm_count;
+    auto even_seg = [&](int want) {
+        int sg = (a.h + want - 1) / want;
+        int sr = (((a.h + sg - 1) / sg) + 7) & ~7;          // even segments (1080 rows: 5 x 216 instead of 4 x 256 + 56)
+        return sr < 8 ? 8 : sr;
+    };
+    auto cost = [&](int sr) {
+        const long long sg = (a.h + sr - 1) / sr, it = (long long) strips * sg * n_frames;
+        const long long per = sr / 8 + 2;
+        const long long rounds = (it + ctas - 1) / ctas;
+        const long long balanced = (it * per + ctas - 1) / ctas + per / 2;   // many items: the tail is about half an item
+        return it <= 4 * ctas ? rounds * per : balanced;
+    };
+    int seg = even_seg(256);
+    for (int want : {128, 64, 32}) {
+        const int sr = even_seg(want);
+        if (cost(sr) < cost(seg)) seg = sr;
+    }
+    {
+        const long long per_col = ctas / ((long long) strips * n_frames);      // segments per strip that still fit one round
+        if (per_col >= 1) {
+            const int sr = even_seg((int) ((a.h + per_col - 1) / per_col));
+            if ((long long) strips * ((a.h + sr - 1) / sr) * n_frames <= ctas && cost(sr) < cost(seg)) seg = sr;
+        }
+    }
+    const int segs = (a.h + seg - 1) / seg;
     const long long items = (long long) strips * segs * n_frames;
     if (items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int grid = (int) (items < 2LL * sm_count ? items : 2LL * sm_count);
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), stream);
-    if (e != cudaSuccess) return e;
 #define DCTC_TC_LAUNCH(U, C)                                                                                           \
     do {                                                                                                               \
         cudaError_t ea = cudaFuncSetAttribute(dctc_k1_tc8_kernel<U, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAD_SMEM); \

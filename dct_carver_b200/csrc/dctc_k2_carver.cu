@@ -278,6 +278,8 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
                                                   // TMA: followed by warps x nst stages x DP_SR rows x STRIP energies
     __shared__ __align__(8) unsigned long long ebar[DP_MAXW][DP_NST_MAX];
     __shared__ __align__(8) unsigned long long hbar[DP_MAXW][2];   // halo exchange: per warp and slot, counts the neighbours' bytes
+    __shared__ __align__(8) unsigned long long rbar;               // CTA 0: counts the strips' last-row minima (8 bytes each)
+    __shared__ __align__(8) int2 red_p[DP_CL * DP_MAXW];           // CTA 0: (value bits, column) per strip
     __shared__ float red_v[DP_CL * DP_MAXW];      // per-strip minima, gathered in CTA 0 through distributed shared memory
     __shared__ int red_i[DP_CL * DP_MAXW];
     __shared__ __align__(16) float win[2][32][DP_WINP];
@@ -356,6 +358,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&hbar[tid >> 5][0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&hbar[tid >> 5][1])) : "memory");
+        if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&rbar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -550,13 +553,27 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
     }
-    if (lane == 0) { dp_st_cluster_f32(dp_map(&red_v[warp], 0u), bv); dp_st_cluster_s32(dp_map(&red_i[warp], 0u), bi); }
-    dp_cluster_sync();   // release/acquire at cluster scope: also orders every CTA's global writes of the cumulative plane
+    if (xlast) {
+        // parallel back-track follows in other kernels (the launch boundary publishes the cumulative plane): the strips'
+        // minima travel to CTA 0 like the halos (st.async + mbarrier), no cluster barrier and no memory fence at the end
+        if (lane == 0)
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                         ::"r"(dp_map(&red_p[warp], 0u)), "r"(__float_as_uint(bv)), "r"(bi), "r"(dp_map(&rbar, 0u)) : "memory");
+        if (rank == 0 && tid < 32) {
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dp_smem_u32(&rbar)), "r"((uint32_t) nwarps * 8u) : "memory");
+            dp_mbar_wait(dp_smem_u32(&rbar), 0u);
+        }
+    } else {
+        if (lane == 0) { dp_st_cluster_f32(dp_map(&red_v[warp], 0u), bv); dp_st_cluster_s32(dp_map(&red_i[warp], 0u), bi); }
+        dp_cluster_sync();   // release/acquire at cluster scope: also orders every CTA's global writes of the cumulative plane
+    }
     if (rank == 0 && tid < 32) {
         bv = INF;
         bi = 0x7fffffff;
         for (int i = tid; i < nwarps; i += 32) {   // strips in ascending column order: strict < keeps the leftmost
-            if (red_i[i] != 0x7fffffff && (bi == 0x7fffffff || red_v[i] < bv)) { bv = red_v[i]; bi = red_i[i]; }
+            const float rv = xlast ? __int_as_float(red_p[i].x) : red_v[i];
+            const int ri = xlast ? red_p[i].y : red_i[i];
+            if (ri != 0x7fffffff && (bi == 0x7fffffff || rv < bv)) { bv = rv; bi = ri; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -647,8 +664,9 @@ __global__ void __launch_bounds__(128) dctc_seam_jump_kernel(const float* __rest
 }
 
 constexpr int TR_WIN = 72;                            // walk window: columns x-34 .. x+37 around the block's bottom column
+constexpr int TR_THREADS = 256;
 
-__global__ void __launch_bounds__(128) dctc_seam_trace_kernel(const float* __restrict__ mplane, size_t m_pitch, int w, int h,
+__global__ void __launch_bounds__(TR_THREADS) dctc_seam_trace_kernel(const float* __restrict__ mplane, size_t m_pitch, int w, int h,
                                                               const int8_t* __restrict__ jump, size_t j_pitch,
                                                               const int* __restrict__ xlast, int* __restrict__ seam,
                                                               int* __restrict__ seam_log)
@@ -656,23 +674,34 @@ __global__ void __launch_bounds__(128) dctc_seam_trace_kernel(const float* __res
     extern __shared__ __align__(16) unsigned char tr_smem[];
     __shared__ __align__(16) float win[JB][TR_WIN + 8];
     __shared__ int xb_s;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = blockIdx.x;
     const int x0 = *xlast;
-    // cone of block j: bottom columns x0 - 32 j .. x0 + 32 j, staged at offset 32 j (j - 1) + j
-    int8_t* cone = reinterpret_cast<int8_t*>(tr_smem);
-    for (int j = 0; j < k; j++) {
-        const int off = 32 * j * (j - 1) + j, lo = x0 - JB * j, n = 2 * JB * j + 1;
-        const int8_t* srcj = jump + (size_t) j * j_pitch;
-        for (int i = tid; i < n; i += 128) {
-            const int x = lo + i;
-            cone[off + i] = (x >= 0 && x < w) ? srcj[x] : (int8_t) 0;
+    // Cone of block j: its bottom column can be x0 - 32 j .. x0 + 32 j.  The entries are staged as aligned 16-byte
+    // chunks (at most 4 j + 3 per row, at byte offset 32 j^2 + 16 j of the cone buffer); warp w takes the rows
+    // j = w, w + 8, ... and issues all chunks of a row before it stores any of them, so the loads of a row (and of the
+    // other warps' rows) are in flight together instead of one L2 round trip per iteration.
+    for (int j = wid; j < k; j += TR_THREADS / 32) {
+        const int a0 = max(0, x0 - JB * j) & ~15;
+        const int last = min(w - 1, x0 + JB * j);
+        const int nchunk = ((last - a0) >> 4) + 1;                          // <= 4 j + 3
+        const uint4* srcj = reinterpret_cast<const uint4*>(jump + (size_t) j * j_pitch + a0);
+        uint4* dstj = reinterpret_cast<uint4*>(tr_smem + 32 * j * j + 16 * j);
+        for (int c0 = 0; c0 < nchunk; c0 += 160) {                          // (one pass up to 1080 rows, two beyond)
+            uint4 v[5];
+#pragma unroll
+            for (int i = 0; i < 5; i++)
+                if (c0 + lane + 32 * i < nchunk) v[i] = __ldcg(srcj + c0 + lane + 32 * i);
+#pragma unroll
+            for (int i = 0; i < 5; i++)
+                if (c0 + lane + 32 * i < nchunk) dstj[c0 + lane + 32 * i] = v[i];
         }
     }
     __syncthreads();
     if (tid == 0) {
+        const int8_t* cone = reinterpret_cast<const int8_t*>(tr_smem);
         int x = x0;
-        for (int j = 0; j < k; j++) x += cone[32 * j * (j - 1) + j + (x - (x0 - JB * j))];
+        for (int j = 0; j < k; j++) x += cone[32 * j * j + 16 * j + (x - (max(0, x0 - JB * j) & ~15))];
         xb_s = x;
     }
     __syncthreads();
@@ -682,7 +711,7 @@ __global__ void __launch_bounds__(128) dctc_seam_trace_kernel(const float* __res
     const int max_base = (int) m_pitch - TR_WIN;
     int base = (x - 34) & ~3;
     base = base < 0 ? 0 : (base > max_base ? max_base : base);
-    for (int idx = tid; idx < steps * (TR_WIN / 4); idx += 128) {
+    for (int idx = tid; idx < steps * (TR_WIN / 4); idx += TR_THREADS) {
         const int i = idx / (TR_WIN / 4), c = idx - i * (TR_WIN / 4);
         const float* src = mplane + (size_t) (yb - 1 - i) * m_pitch + base + 4 * c;
         *reinterpret_cast<float4*>(&win[i][4 + 4 * c]) = __ldcg(reinterpret_cast<const float4*>(src));
@@ -1222,7 +1251,11 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     // strip geometry: 128*P columns per warp, 128*P - 2*DP_R published; the strips are spread over a cluster of DP_CL CTAs
     const int wcur = ctx->c_w;
     const int cap = DP_CL * DP_MAXW;
-    const int P = wcur <= cap * (128 - 2 * DP_R) ? 1 : wcur <= cap * (256 - 2 * DP_R) ? 2 : 4;
+    int P = wcur <= cap * (128 - 2 * DP_R) ? 1 : wcur <= cap * (256 - 2 * DP_R) ? 2 : 4;
+    if (const char* ep = getenv("DCTC_DP_P")) {   // timing experiments: wider strips than the width needs
+        const int want = atoi(ep);
+        if ((want == 2 || want == 4) && want > P) P = want;
+    }
     const int wout = 128 * P - 2 * DP_R;
     const int strips = (wcur + wout - 1) / wout;
     const int wpc = (strips + DP_CL - 1) / DP_CL;
@@ -1283,11 +1316,12 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
     // parallel back-track (jump + trace kernels): needs the jump plane and a cone of jump entries in shared memory that
     // grows with the square of the number of 32-row blocks; very tall images keep the serial walk of the DP kernel
     const int nb = (h - 1 + JB - 1) / JB;
-    const size_t cone_smem = nb > 0 ? (size_t) 32 * (nb - 1) * (nb - 2 > 0 ? nb - 2 : 0) + nb + 16 : 16;
+    const size_t cone_smem = nb > 0 ? (size_t) 32 * (nb - 1) * (nb - 1) + 16 * (size_t) (nb - 1) + 16 : 16;   // rows j < nb-1: 16 (4 j + 3) bytes each
+    const size_t j_pitch = (m_pitch + 15) & ~(size_t) 15;    // jump rows start 16-byte aligned (staged in 16-byte chunks)
     const bool par_bt = nb > 0 && cone_smem <= 200 * 1024 && !getenv("DCTC_SERIAL_BACKTRACK");
     int* const xlast = par_bt ? ctx->c_band + 4 : nullptr;
     if (par_bt) {
-        if (!ctx->c_dir) CK(ctx, cudaMalloc((void**) &ctx->c_dir, (size_t) nb * m_pitch));
+        if (!ctx->c_dir) CK(ctx, cudaMalloc((void**) &ctx->c_dir, (size_t) nb * j_pitch));
         if (cone_smem > 40 * 1024)
             CK(ctx, cudaFuncSetAttribute(dctc_seam_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cone_smem));
     }
@@ -1305,8 +1339,8 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
             dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr, nst, tmap, use_tmap, xlast);
             if (par_bt) {
                 const int js = (w_old + 63) / 64;
-                dctc_seam_jump_kernel<<<dim3((js + 3) / 4, nb), 128, 0, ctx->stream>>>(ctx->c_m, m_pitch, w_old, h, ctx->c_dir, m_pitch, js);
-                dctc_seam_trace_kernel<<<nb, 128, cone_smem, ctx->stream>>>(ctx->c_m, m_pitch, w_old, h, ctx->c_dir, m_pitch, xlast, ctx->c_seam, log_s);
+                dctc_seam_jump_kernel<<<dim3((js + 3) / 4, nb), 128, 0, ctx->stream>>>(ctx->c_m, m_pitch, w_old, h, ctx->c_dir, j_pitch, js);
+                dctc_seam_trace_kernel<<<nb, TR_THREADS, cone_smem, ctx->stream>>>(ctx->c_m, m_pitch, w_old, h, ctx->c_dir, j_pitch, xlast, ctx->c_seam, log_s);
                 ctx->launches += 2;
             }
         }
