@@ -277,9 +277,15 @@ def config_c3(ctx_args, hbm_peak):
     t0 = time.perf_counter()
     ctx.carver_load(img)
     t_load = time.perf_counter() - t0
+    # the loop in two calls: the first one also allocates the session's cumulative / jump planes and the seam log, the
+    # second one (240 seams, device events around it) is the steady state that us_per_seam quotes
+    tw = time.perf_counter()
+    first = ctx.carver_resize_width(n // 2)
     ctx.timer_begin()
-    seams = ctx.carver_resize_width(n)
-    ms_loop = ctx.timer_end()
+    second = ctx.carver_resize_width(n - n // 2)
+    ms_second = ctx.timer_end()
+    ms_loop = 1e3 * (time.perf_counter() - tw)
+    seams = np.concatenate([first, second])
     launches = ctx.launches - l0
     t1 = time.perf_counter()
     r2 = host.render(img, -n, 8, 0.5, 0.5, ctx=ctx, device_loop=True)          # the drop-in call a reference user makes
@@ -292,7 +298,8 @@ def config_c3(ctx_args, hbm_peak):
     ctx.close()
     band_px = n * h * 10   # ~ (2r + spread) x h pixels recomputed per seam
     return {"workload": "1920x1080 RGB -> 1440x1080, 480 vertical seams, blocksize 8, device-resident seam loop",
-            "us_per_seam": 1e3 * ms_loop / n, "seam_loop_s": ms_loop * 1e-3, "load_and_full_map_s": t_load,
+            "us_per_seam": 1e3 * ms_second / (n - n // 2), "us_per_seam_incl_first_call_allocations": 1e3 * ms_loop / n,
+            "seam_loop_s": ms_loop * 1e-3, "load_and_full_map_s": t_load,
             "dctc_render_total_s": t_render, "host_carver_total_s": t_host, "gpu_launches": launches,
             "seams_identical_to_host_carver": same,
             "band_Mpix_s": band_px / (ms_loop * 1e-3) / 1e6,
@@ -451,7 +458,7 @@ def main():
             te = float(t.item())
         e2e = {"value": Fe * w * h * world / te / 1e6, "unit": UNIT, "h2d_bytes_per_step": Fe * h * w * ch * world,
                "d2h_bytes_per_step": Fe * h * w * 4 * world, "frames_per_step": Fe * world, "steps_timed": ke,
-               "api": "dctc_energy_batch (host buffers, 3-slot H2D/compute/D2H overlap)"}
+               "api": "dctc_energy_batch (host buffers, 4-slot H2D/compute/D2H overlap)"}
         assert float(np.abs(h_out[0]).max()) > 0.0
         # the ceiling of that path: pinned-copy bandwidth with every rank copying at the same time
         barrier()
@@ -474,6 +481,14 @@ def main():
         if d_in is not None:
             # C2 as ONE image per launch (the 512 resident frames are the rotation pool)
             if world == 1:
+                # the same kernel in a short burst from a cool board (0.5 s pause, then 20 launches of 16 frames = 16 ms):
+                # max boost clocks, no power cap -- the number round 1 reported as the headline
+                time.sleep(0.5)
+                bs = ClockSampler(local_rank)
+                bs.start()
+                burst = frames_config(ctx, timer, w, h, ch, F, 16, 20, hbm_peak, SEED, d_in=d_in, d_out=d_out)
+                burst["clocks"] = bs.stop()
+                configs["C2_burst_16_frames"] = burst
                 configs["C2_one_frame_per_launch"] = frames_config(ctx, timer, w, h, ch, F, 1, 200, hbm_peak, SEED, d_in=d_in, d_out=d_out)
                 ctx.set_params(8, 0.8, 0.2)
                 configs["C2_weights_0.8_0.2"] = frames_config(ctx, timer, w, h, ch, F, 64, 5, hbm_peak, SEED, d_in=d_in, d_out=d_out)

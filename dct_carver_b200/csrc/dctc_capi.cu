@@ -301,8 +301,11 @@ int dctc_energy_batch(dctc_context* ctx, const uint8_t* imgs, int n_frames, size
     for (int f = 0; f < n_frames; f++) {
         const int s = f % DCTC_SLOTS;
         if (f >= DCTC_SLOTS) CK(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[s], 0));  // slot input consumed
-        CK(ctx, cudaMemcpy2DAsync(ctx->d_in[s], d_pitch, imgs + (size_t) f * frame_stride, pitch, row_bytes, h,
-                                  cudaMemcpyHostToDevice, ctx->s_in));
+        if (pitch == row_bytes && d_pitch == row_bytes)   // contiguous on both sides: one linear copy per frame
+            CK(ctx, cudaMemcpyAsync(ctx->d_in[s], imgs + (size_t) f * frame_stride, row_bytes * (size_t) h, cudaMemcpyHostToDevice, ctx->s_in));
+        else
+            CK(ctx, cudaMemcpy2DAsync(ctx->d_in[s], d_pitch, imgs + (size_t) f * frame_stride, pitch, row_bytes, h,
+                                      cudaMemcpyHostToDevice, ctx->s_in));
         CK(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
         CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
         if (f >= DCTC_SLOTS) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));  // slot output drained

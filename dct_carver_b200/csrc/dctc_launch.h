@@ -15,7 +15,7 @@ cudaError_t dctc_launch_synth(uint8_t* d_img, int n_frames, size_t frame_stride,
                               size_t pitch, uint32_t seed, int pattern, int first_frame, int y_offset,
                               cudaStream_t stream);
 
-constexpr int DCTC_SLOTS = 3;
+constexpr int DCTC_SLOTS = 4;   // device staging slots of the host-buffer batch call (H2D, kernel and D2H of different frames overlap)
 constexpr int DCTC_TC_COUNTERS = 64;
 
 struct dctc_context {

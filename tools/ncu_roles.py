@@ -2,7 +2,7 @@
 """Per-role instruction and stall accounting of the warp-specialised K1-TC kernel from an ncu source page:
    ncu -i prof.ncu-rep --page source --csv > src.csv ; python tools/ncu_roles.py src.csv <pixels in the launch>
 Roles are recognised by the SETMAXREG instructions that open each warpgroup's code region (producers, consumers,
-MMA issuer + converters); inside the last region the MMA warp's code is the part that contains UTCHMMA."""
+MMA issuer + converters); the MMA issuer warp and the converter warps share the last region."""
 import csv
 import sys
 from collections import Counter, defaultdict
@@ -22,7 +22,7 @@ def main():
     marks = [i for i, r in enumerate(ins) if "SETMAXREG" in r[col["Source"]]]
     # each setmaxnreg is a small retry loop: keep the first of each cluster
     starts = [m for k, m in enumerate(marks) if k == 0 or m - marks[k - 1] > 8]
-    names = ["prologue", "producers (x-pass, split, tcgen05.st)", "consumers (tcgen05.ld, fold, store)", "MMA issuer + converters"]
+    names = ["prologue", "producers (x-pass, split, tcgen05.st)", "consumers (tcgen05.ld, fold, store)", "MMA issuer (1 warp) + converters (3 warps: cp.async, luma)"]
     bounds = [0] + starts + [len(ins)]
     stall_cols = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
     total_exec = 0
@@ -30,16 +30,7 @@ def main():
     for k in range(len(bounds) - 1):
         seg = ins[bounds[k]:bounds[k + 1]]
         name = names[k] if k < len(names) else "region %d" % k
-        if k == 3:
-            # split at the first converter-only instruction: the MMA loop precedes the converter loop; find last UTCHMMA-related
-            last_mma = max(i for i, r in enumerate(seg) if "UTCHMMA" in r[col["Source"]] or "UTCBAR" in r[col["Source"]])
-            # the MMA item loop ends at the first unconditional BRA after last_mma
-            end = last_mma
-            while end < len(seg) and not seg[end][col["Source"]].strip().startswith("BRA"):
-                end += 1
-            parts = [("MMA issuer", seg[:end + 1]), ("converters (cp.async, luma)", seg[end + 1:])]
-        else:
-            parts = [(name, seg)]
+        parts = [(name, seg)]   # the MMA issuer warp and the three converter warps share one setmaxnreg region
         for nm, sg in parts:
             ex = sum(float(r[col["Instructions Executed"]] or 0) for r in sg)
             samples = sum(float(r[col["# Samples"]] or 0) for r in sg)
@@ -59,7 +50,7 @@ def main():
             total_exec += ex
     print("total warp instructions %.0f = %.2f lane-instr/px" % (total_exec, total_exec * 32 / npx))
     for nm, ex, samples, st, ops in out:
-        print("\n%-42s %12.0f warp-instr  %6.2f lane-instr/px  %5.1f %%  samples %d" % (nm, ex, ex * 32 / npx, 100 * ex / total_exec, samples))
+        print("\n%-62s %12.0f warp-instr  %6.2f lane-instr/px  %5.1f %%  samples %d" % (nm, ex, ex * 32 / npx, 100 * ex / total_exec, samples))
         print("   top opcodes: " + ", ".join("%s %.2f" % (o, n * 32 / npx) for o, n in ops.most_common(14)))
         tot = sum(st.values()) or 1
         print("   stalls: " + ", ".join("%s %.0f%%" % (c[6:], 100 * v / tot) for c, v in st.most_common(6)))
