@@ -1,4 +1,6 @@
-"""Row-band sharding of one tall image over the GPUs of a box, one process per GPU (BASELINE config 5).
+"""Row-band sharding of one tall image over the GPUs of a box, one process per GPU (BASELINE config 5) -- the round-1
+Python plumbing.  The product path is the C layer now (csrc/dctc_multi.cu: dctc_band_runner_* / dctc_multi_*, mirrored
+by dct_carver_b200.BandRunner / Multi); this module stays for the torch.distributed "exchange" mode and its gloo tests.
 
 Every output pixel needs blocksize/2-1 rows above and blocksize/2 rows below (window offsets -b/2+1..b/2,
 /root/reference/src/render.c:146-147), so a band needs that many rows from each neighbour; the image's own
@@ -59,6 +61,10 @@ class BandRunner:
         self.pitch = w * ch
         self.top_need, self.bot_need = halo_rows(ctx.blocksize)
         self.mode = mode if world > 1 else "single"
+        # every band must be tall enough to serve its neighbours' halos (a kernel reads at most one band away)
+        rows_all = [y1 - y0 for y0, y1 in band_bounds(h, world)]
+        if world > 1 and min(rows_all) < max(self.top_need, self.bot_need):
+            raise ValueError("band thinner than the halo: %d rows, %d needed" % (min(rows_all), max(self.top_need, self.bot_need)))
         self.d_band = ctx.dev_alloc(self.band_rows * self.pitch)
         self.d_out = ctx.dev_alloc(self.band_rows * w * 4)
         # content = rows y0..y1 of the virtual image (y_offset keeps bands consistent across ranks)
@@ -143,6 +149,9 @@ class BandRunner:
         return out
 
     def close(self):
+        if self.dist is not None and self.world > 1:
+            self.ctx.sync()
+            self.dist.barrier()        # no rank frees its band while a neighbour's kernel may still be reading it
         for p in self._peers:
             self.ctx.ipc_close(p)
         self._peers = []
