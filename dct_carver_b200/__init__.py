@@ -21,7 +21,7 @@ KERNEL_AUTO, KERNEL_FP32_TILE, KERNEL_FP32_MARCH, KERNEL_TC_SPLIT = 0, 1, 2, 3
 ABI_SYMBOLS = [
     "dctc_create", "dctc_destroy", "dctc_set_params", "dctc_set_kernel", "dctc_last_cuda_error", "dctc_strerror",
     "dctc_version", "dctc_device_count", "dctc_stream", "dctc_launch_count",
-    "dctc_energy_full", "dctc_energy_full_dev", "dctc_energy_batch_dev", "dctc_energy_band_dev", "dctc_energy_batch",
+    "dctc_energy_full", "dctc_energy_full_dev", "dctc_energy_batch_dev", "dctc_energy_band_dev", "dctc_energy_band_dev_at", "dctc_energy_batch",
     "dctc_carver_load", "dctc_carver_width", "dctc_carver_height", "dctc_carver_energy", "dctc_carve_and_update",
     "dctc_carver_image", "dctc_carver_resize_width", "dctc_carver_enlarge_width", "dctc_carver_set_incremental", "dctc_carver_rebuild_count", "dctc_pixel_energy",
     "dctc_energy_minmax_dev", "dctc_energy_image_dev", "dctc_carver_energy_image", "dctc_preview_energy",
@@ -90,6 +90,7 @@ def lib():
         "dctc_energy_full_dev": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, i32]),
         "dctc_energy_batch_dev": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, vp, sz, sz, i32]),
         "dctc_energy_band_dev": (i32, [vp, vp, i32, i32, i32, sz, vp, i32, sz, vp, i32, sz, vp, sz, i32]),
+        "dctc_energy_band_dev_at": (i32, [vp, vp, i32, i32, i32, i32, sz, vp, i32, sz, vp, i32, sz, vp, sz, i32]),
         "dctc_energy_batch": (i32, [vp, vp, i32, sz, i32, i32, i32, sz, vp, sz]),
         "dctc_carver_load": (i32, [vp, vp, i32, i32, i32, sz]),
         "dctc_carver_width": (i32, [vp]),
@@ -302,11 +303,12 @@ class Context:
                "dctc_energy_batch_dev")
 
     def energy_band_dev(self, d_band, w, rows, ch, pitch, d_top, top_rows, top_pitch, d_bot, bot_rows, bot_pitch, d_out,
-                        out_pitch, sync=False):
-        _check(lib().dctc_energy_band_dev(self._h, C.c_void_p(d_band), w, rows, ch, pitch,
-                                          C.c_void_p(d_top) if d_top else None, top_rows, top_pitch,
-                                          C.c_void_p(d_bot) if d_bot else None, bot_rows, bot_pitch,
-                                          C.c_void_p(d_out), out_pitch, int(sync)), "dctc_energy_band_dev")
+                        out_pitch, sync=False, band_y0=0):
+        """band_y0: image row of the band's first row (dctc_energy_band_dev_at); 0 = dctc_energy_band_dev."""
+        _check(lib().dctc_energy_band_dev_at(self._h, C.c_void_p(d_band), w, rows, band_y0, ch, pitch,
+                                             C.c_void_p(d_top) if d_top else None, top_rows, top_pitch,
+                                             C.c_void_p(d_bot) if d_bot else None, bot_rows, bot_pitch,
+                                             C.c_void_p(d_out), out_pitch, int(sync)), "dctc_energy_band_dev_at")
 
     # -- K2 carver session ----------------------------------------------------------------------------------
     def carver_load(self, img):

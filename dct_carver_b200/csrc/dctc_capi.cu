@@ -177,6 +177,10 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
         e = cudaErrorNotSupported;
         if (ctx->kernel == DCTC_KERNEL_AUTO && !a.seam && !a.preview && (ctx->blocksize == 2 || ctx->blocksize == 4))
             e = dctc_launch_k1_small(a, ctx->blocksize, n_frames, uniform, ctx->sm_count, stream);
+        // block size 16 (compute-bound): full maps run their y-pass on the tensor cores unless the FP32 tile kernel was
+        // asked for explicitly (or the configuration is outside the tensor-core fast path)
+        if (ctx->kernel != DCTC_KERNEL_FP32_TILE && ctx->kernel != DCTC_KERNEL_FP32_MARCH && !a.seam && !a.preview && ctx->blocksize == 16)
+            e = dctc_launch_k1_tc16(a, n_frames, uniform, ctx->tc_counters + (ctx->tc_next++ % DCTC_TC_COUNTERS), ctx->sm_count, stream);
         if (e == cudaErrorNotSupported) e = dctc_launch_k1_tile(a, ctx->blocksize, n_frames, uniform, stream);
         break;
     case DCTC_KERNEL_FP32_MARCH: e = dctc_launch_k1_march8(a, n_frames, uniform, stream); break;
@@ -255,7 +259,15 @@ int dctc_energy_band_dev(dctc_context* ctx, const uint8_t* d_band, int w, int ba
                          const uint8_t* d_top, int top_rows, size_t top_pitch, const uint8_t* d_bot, int bot_rows,
                          size_t bot_pitch, float* d_out, size_t out_pitch, int sync)
 {
-    if (!ctx || !d_band || !d_out) return DCTC_ERR_INVALID;
+    return dctc_energy_band_dev_at(ctx, d_band, w, band_rows, 0, channels, pitch, d_top, top_rows, top_pitch, d_bot, bot_rows, bot_pitch,
+                                   d_out, out_pitch, sync);
+}
+
+int dctc_energy_band_dev_at(dctc_context* ctx, const uint8_t* d_band, int w, int band_rows, int band_y0, int channels, size_t pitch,
+                            const uint8_t* d_top, int top_rows, size_t top_pitch, const uint8_t* d_bot, int bot_rows,
+                            size_t bot_pitch, float* d_out, size_t out_pitch, int sync)
+{
+    if (!ctx || !d_band || !d_out || band_y0 < 0) return DCTC_ERR_INVALID;
     int rc = check_image(w, band_rows, channels, pitch);
     if (rc) return rc;
     if (out_pitch < (size_t) w || top_rows < 0 || bot_rows < 0) return DCTC_ERR_INVALID;
@@ -268,6 +280,7 @@ int dctc_energy_band_dev(dctc_context* ctx, const uint8_t* d_band, int w, int ba
     plain_args(a, d_band, w, band_rows, channels, pitch, d_out, out_pitch);
     a.top = d_top; a.top_rows = d_top ? top_rows : 0; a.top_pitch = top_pitch;
     a.bot = d_bot; a.bot_rows = d_bot ? bot_rows : 0; a.bot_pitch = bot_pitch;
+    a.row_origin = band_y0;
     rc = dctc_run_k1(ctx, a, 1, ctx->stream);
     if (rc) return rc;
     if (sync) CK(ctx, cudaStreamSynchronize(ctx->stream));

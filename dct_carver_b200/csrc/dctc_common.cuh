@@ -30,6 +30,9 @@ struct DctcK1Args {
     // preview operator (dct_energy_preview_rows, src/render.c:31-60): window offsets -(C-1) .. b-C with C = (b-1)/2
     // (src/dct.h:8-9), BT.601 byte luminance (src/render.h:5), first transform index walks y (tile kernel only)
     int preview;
+    // Global row of band row 0 (row bands of a taller image; 0 for whole images).  Only K1-TC16 uses it: its 16-row
+    // steps are anchored to the global row grid, so a pixel's FP32 accumulation order does not depend on the band cut.
+    int row_origin;
 };
 
 // Band limits of row y for a removed seam (seam[] in the coordinates before removal, w = width after removal).

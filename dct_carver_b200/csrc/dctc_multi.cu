@@ -163,8 +163,8 @@ static int band_upload(DctcBand& b, const uint8_t* rows_host, size_t host_pitch)
 
 static int band_energy(DctcBand& b, int sync)
 {
-    return dctc_energy_band_dev(b.ctx, b.d_band, b.w, b.rows, b.ch, b.pitch, b.d_top, b.d_top ? b.top_need : 0, b.pitch, b.d_bot,
-                                b.d_bot ? b.bot_need : 0, b.pitch, b.d_out, (size_t) b.w, sync);
+    return dctc_energy_band_dev_at(b.ctx, b.d_band, b.w, b.rows, b.y0, b.ch, b.pitch, b.d_top, b.d_top ? b.top_need : 0, b.pitch, b.d_bot,
+                                   b.d_bot ? b.bot_need : 0, b.pitch, b.d_out, (size_t) b.w, sync);
 }
 
 static int band_download(DctcBand& b, float* out_rows)

@@ -114,7 +114,7 @@ class BandRunner:
         if self.mode == "exchange":
             self._exchange()
         c.energy_band_dev(self.d_band, self.w, self.band_rows, self.ch, self.pitch, self.d_top, self.top_rows,
-                          self.pitch, self.d_bot, self.bot_rows, self.pitch, self.d_out, self.w)
+                          self.pitch, self.d_bot, self.bot_rows, self.pitch, self.d_out, self.w, band_y0=self.y0)
 
     def _exchange(self):
         import torch

@@ -119,6 +119,15 @@ int dctc_energy_band_dev(dctc_context *ctx, const uint8_t *d_band, int w, int ba
                          const uint8_t *d_bot, int bot_rows, size_t bot_pitch_bytes, float *d_out,
                          size_t out_pitch, int sync);
 
+/* Same for a caller that knows where the band sits in the whole image: band_y0 = image row of the band's first row.
+ * The block-size-16 tensor-core kernel anchors its 16-row accumulation steps to the image's row grid, so with band_y0
+ * given the band's map is bit-identical to the rows a single full-image call produces, however the image is cut
+ * (dctc_energy_band_dev is band_y0 = 0; every other kernel ignores it).  The multi-GPU layer below passes it. */
+int dctc_energy_band_dev_at(dctc_context *ctx, const uint8_t *d_band, int w, int band_rows, int band_y0, int channels,
+                            size_t pitch_bytes, const uint8_t *d_top, int top_rows, size_t top_pitch_bytes,
+                            const uint8_t *d_bot, int bot_rows, size_t bot_pitch_bytes, float *d_out,
+                            size_t out_pitch, int sync);
+
 /* Host-buffer batch through pinned staging with copy/compute overlap (what bench.py's e2e measures). */
 int dctc_energy_batch(dctc_context *ctx, const uint8_t *imgs, int n_frames, size_t frame_stride_bytes, int w,
                       int h, int channels, size_t pitch_bytes, float *out, size_t out_frame_stride);
