@@ -36,6 +36,21 @@
 
 namespace {
 
+// -DDCTC_TC16_TIMING: per-role cycle accounting (clock64 deltas between marks), printed by CTA 0 when it retires
+#ifdef DCTC_TC16_TIMING
+struct TT { long long acc[5]; long long last; };
+#define TT_DECL() TT tt = {{0, 0, 0, 0, 0}, clock64()}; const long long tt_start = tt.last
+#define TT_ACC(k) { const long long tt_now = clock64(); tt.acc[k] += tt_now - tt.last; tt.last = tt_now; }
+#define TT_REPORT(role, cond)                                                                                          \
+    if (blockIdx.x == 0 && (cond))                                                                                     \
+        printf("role %d: total %lld clk, marks %lld %lld %lld %lld %lld\n", role, clock64() - tt_start, tt.acc[0], tt.acc[1], tt.acc[2], tt.acc[3], tt.acc[4])
+#else
+struct TT {};
+#define TT_DECL() TT tt
+#define TT_ACC(k)
+#define TT_REPORT(role, cond)
+#endif
+
 constexpr int PW = 64;             // pixel columns per CTA
 constexpr int LW = 80;             // staged luma row: index i <-> column x0 - 8 + i (1..79 are read)
 constexpr int NQ = LW / 4;         // 4-pixel conversion tasks per row pair
@@ -50,7 +65,9 @@ struct alignas(128) Tc16Smem {
     __half B[8][2048];               // Tz sub-operands [(v*2 + kh)*2 + h]: v = Bh/Bl, kh = K half (group), h = k2 half (tile)
     float2 L[2][8][LW];              // scaled luma of two groups: [buffer][row pair][column], .x = even row
     uint32_t stash[8][2][8][128];    // operands of one group: [m][hi|-lo][row pair][lane]
-    float comb[2][4][16][PW];        // per-step partial maxima: [step parity][tile*2 + k1 parity][row][column]
+    float comb[2][8][16][PW];        // per-step partials: [step parity][plane][row][column]; planes 0-3: maxima of
+                                     // (tile*2 + k1 parity); edges != textures also: 4 |T[0][1]|, 5/6 max|T[0][2..]| of
+                                     // tile 0 / 1, 7 |T[1][0]| (the quantities of DctcTracker<false>)
     uint64_t bar_a_full[8], bar_a_free[8], bar_d_full[2];
     uint32_t tmem_base;
     int work;
@@ -212,11 +229,12 @@ __device__ __forceinline__ void split_pair(float2 x, uint32_t& hi, uint32_t& nlo
 // x-pass + split of group g (rows staged in s.L[g&1]) for this lane's parity, parked in s.stash; then, m by m, the
 // TMEM stores into ring slot g&1 as soon as the MMAs of step g-2 have consumed that m
 template <int PARITY>
-__device__ __forceinline__ void produce_group(Tc16Smem& s, int g, int lane128, uint32_t tmem_lane)
+__device__ __forceinline__ void produce_group(Tc16Smem& s, int g, int lane128, uint32_t tmem_lane, TT& tt)
 {
+    (void) tt;
     const int px = lane128 & (PW - 1);
     const float2 (*Lg)[LW] = s.L[g & 1];
-#pragma unroll 1
+#pragma unroll 2
     for (int p = 0; p < 8; p++) {
         float2 v[16], X[16];
 #pragma unroll
@@ -231,16 +249,20 @@ __device__ __forceinline__ void produce_group(Tc16Smem& s, int g, int lane128, u
             s.stash[m][1][p][lane128] = nlo;
         }
     }
+    TT_ACC(2);
     const uint32_t ta = tmem_lane + TM_A + (uint32_t) (g & 1) * 8u;
-#pragma unroll 1
+    // the parked operands of m+1 are fetched while the stores of m complete
+    uint32_t o[2][8], on[2][8];
+#pragma unroll
+    for (int part = 0; part < 2; part++)
+#pragma unroll
+        for (int p = 0; p < 8; p++) o[part][p] = s.stash[0][part][p][lane128];
+#pragma unroll
     for (int m = 0; m < 8; m++) {
-        uint32_t o[2][8];
-#pragma unroll
-        for (int part = 0; part < 2; part++)
-#pragma unroll
-            for (int p = 0; p < 8; p++) o[part][p] = s.stash[m][part][p][lane128];
         if (g >= 2) {
+            TT_ACC(3);
             mbar_wait(smem_u32(&s.bar_a_free[m]), (uint32_t) (g & 1), 100 + m);   // completion g-2 of this barrier
+            TT_ACC(4);
             tc_fence_after();
         }
 #pragma unroll
@@ -249,6 +271,12 @@ __device__ __forceinline__ void produce_group(Tc16Smem& s, int g, int lane128, u
             tmem_st_x4(t, o[part][0], o[part][1], o[part][2], o[part][3]);
             tmem_st_x4(t + 4u, o[part][4], o[part][5], o[part][6], o[part][7]);
         }
+        if (m < 7) {
+#pragma unroll
+            for (int part = 0; part < 2; part++)
+#pragma unroll
+                for (int p = 0; p < 8; p++) on[part][p] = s.stash[m + 1][part][p][lane128];
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -256,6 +284,10 @@ __device__ __forceinline__ void produce_group(Tc16Smem& s, int g, int lane128, u
         // covers all earlier stores).  Completion j of this barrier is group j+1, which needs the "consumed" commit of
         // step j-1, issued after the MMA warp's wait for completion j-1: never more than one completion ahead.
         if (g >= 1 && (lane128 & 31) == 0) mbar_arrive(smem_u32(&s.bar_a_full[m]));   // 4 arrivals (one per producer warp)
+#pragma unroll
+        for (int part = 0; part < 2; part++)
+#pragma unroll
+            for (int p = 0; p < 8; p++) o[part][p] = on[part][p];
     }
 }
 
@@ -276,7 +308,34 @@ __device__ __forceinline__ void fold_tile(const uint32_t (&v)[128], float (&mx)[
     }
 }
 
-template <int CH>
+// edges != textures (last-arg-max class rule, DctcTracker<false>): the m = 0 tiles hold the row k1 = 0 (parity 0) and
+// k1 = 1 (parity 1) of the coefficient matrix, whose entries the rule treats separately.  They are parked in shared
+// memory right away (planes 4-7 of the step's comb buffer); everything else folds into the plain maximum Z.
+//   KIND 0: k1 = 0, k2 = 0..7:  A = |T[0][1]| -> plane 4, max|T[0][2..7]| -> plane 5, (0,0) skipped
+//   KIND 1: k1 = 0, k2 = 8..15: max -> plane 6
+//   KIND 2: k1 = 1, k2 = 0..7:  Bv = |T[1][0]| -> plane 7, the rest -> Z
+template <int KIND>
+__device__ __forceinline__ void fold_tile_class(const uint32_t (&v)[128], float (&mx)[16], float (*__restrict__ cb)[16][PW], int px)
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) f[k] = fabsf(__uint_as_float(v[i * 8 + k]));
+        const float m27 = fmaxf(fmaxf(f[2], fmaxf(f[3], f[4])), fmaxf(f[5], fmaxf(f[6], f[7])));
+        if (KIND == 0) {
+            cb[4][i][px] = f[1];
+            cb[5][i][px] = m27;
+        } else if (KIND == 1) {
+            cb[6][i][px] = fmaxf(m27, fmaxf(f[0], f[1]));
+        } else {
+            cb[7][i][px] = f[0];
+            mx[i] = fmaxf(mx[i], fmaxf(m27, f[1]));
+        }
+    }
+}
+
+template <bool UNIFORM, int CH>
 __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1Args a, int seg_rows, int strips, int segs, int n_items,
                                                                      int phase, int* __restrict__ counter)
 {
@@ -347,17 +406,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
         float* __restrict__ out = a.out + (size_t) frame * a.out_frame_stride;                                         \
         (void) tmem; (void) tmem_lane; (void) x0; (void) y1; (void) img; (void) out;
 
+    TT_DECL();
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
         DCTC16_ITEM_LOOP
         // ===== producers: group g = virtual rows Y0-7+16g .. Y0+8+16g; step j consumes groups j and j+1 =====
         for (int g = 0; g <= nsteps; g++) {
+            TT_ACC(0);
             bar_lfull_sync(g & 1);
-            if (warp < 2) produce_group<0>(s, g, tid, tmem_lane);
-            else produce_group<1>(s, g, tid, tmem_lane);
+            TT_ACC(1);
+            if (warp < 2) produce_group<0>(s, g, tid, tmem_lane, tt);
+            else produce_group<1>(s, g, tid, tmem_lane, tt);
+            TT_ACC(3);
         }
         end_item();
         }
+        TT_REPORT(0, tid == 0);
     } else if (warp < 12) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
         DCTC16_ITEM_LOOP
@@ -366,14 +430,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
         const int lane128 = tid & 127;
         const int px = lane128 & (PW - 1), parity = lane128 >> 6;
         const int ctid = tid - 128;                            // 0..255
-        const float wgt = a.w_textures * LUMA_WEIGHT_SCALE;
+        const float wgt = a.w_textures * LUMA_WEIGHT_SCALE, wge = a.w_edges * LUMA_WEIGHT_SCALE;
+        (void) wge;
         for (int st = 0; st < nsteps; st++) {
             float mx[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) mx[i] = 0.0f;
 #pragma unroll 1
             for (int m = 0; m < 8; m++) {
+                TT_ACC(0);
                 mbar_wait(smem_u32(&s.bar_d_full[h]), (uint32_t) (m & 1), 200 + 10 * h + m);   // completion 8 st + m
+                TT_ACC(1);
                 tc_fence_after();
                 uint32_t v[128];
                 const uint32_t td = tmem_lane + TM_D + 128u * (uint32_t) h;
@@ -383,9 +450,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
                 tmem_ld_x32(td + 96u, v + 96);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
+                TT_ACC(2);
                 bar_tile_arrive(h);
-                if (m == 0 && h == 0 && parity == 0) fold_tile<true>(v, mx);
-                else fold_tile<false>(v, mx);
+                if (UNIFORM) {
+                    if (m == 0 && h == 0 && parity == 0) fold_tile<true>(v, mx);
+                    else fold_tile<false>(v, mx);
+                } else {
+                    if (m == 0 && parity == 0) {
+                        if (h == 0) fold_tile_class<0>(v, mx, s.comb[st & 1], px);
+                        else fold_tile_class<1>(v, mx, s.comb[st & 1], px);
+                    } else if (m == 0 && h == 0) {
+                        fold_tile_class<2>(v, mx, s.comb[st & 1], px);
+                    } else {
+                        fold_tile<false>(v, mx);
+                    }
+                }
+                TT_ACC(3);
             }
             float (*cb)[16][PW] = s.comb[st & 1];
 #pragma unroll
@@ -396,13 +476,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
             for (int q = 0; q < 4; q++) {
                 const int idx = ctid + 256 * q;
                 const int i = idx >> 6, c = idx & (PW - 1);
-                const float e = fmaxf(fmaxf(cb[0][i][c], cb[1][i][c]), fmaxf(cb[2][i][c], cb[3][i][c]));
+                const float z = fmaxf(fmaxf(cb[0][i][c], cb[1][i][c]), fmaxf(cb[2][i][c], cb[3][i][c]));
+                float e;
+                if (UNIFORM) {
+                    e = z * wgt;
+                } else {   // DctcTracker<false>::result
+                    const float av = cb[4][i][c], mm = fmaxf(cb[5][i][c], cb[6][i][c]), bv = cb[7][i][c];
+                    const float am = fmaxf(av, mm);
+                    const float top = fmaxf(fmaxf(am, bv), z);
+                    const bool tex = (z >= fmaxf(am, bv)) || (!(bv >= am) && (mm >= av));
+                    e = top * (tex ? wgt : wge);
+                }
                 const int gy = gy0 + i, gx = x0 + c;
-                if (gy >= 0 && gy < y1 && gx < a.w) out[(size_t) gy * a.out_pitch + gx] = e * wgt;
+                if (gy >= 0 && gy < y1 && gx < a.w) out[(size_t) gy * a.out_pitch + gx] = e;
             }
         }
         end_item();
         }
+        TT_REPORT(1, tid == 128 || tid == 256);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 12) {
@@ -414,11 +505,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
             const uint32_t so = (uint32_t) (st & 1) * 8u, sn = so ^ 8u;   // ring slots of the older / newer group
 #pragma unroll 1
             for (int m = 0; m < 8; m++) {
+                TT_ACC(0);
                 mbar_wait(smem_u32(&s.bar_a_full[m]), (uint32_t) (st & 1), 400 + m);    // completion st: groups <= st+1 stored
+                TT_ACC(1);
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
+                    TT_ACC(1);
                     if (st > 0 || m > 0) bar_tile_sync(h);     // the consumers have loaded the previous contents of tile h
+                    TT_ACC(2);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t d = tmem + TM_D + 128u * (uint32_t) h;
@@ -435,6 +530,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
                         if (h == 1 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free[m]));   // waited on by the producers of group st+2
                     }
                     __syncwarp();
+                    TT_ACC(3);
                 }
             }
         }
@@ -443,6 +539,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
         bar_tile_sync(1);
         end_item();
         }
+        TT_REPORT(2, tid == 384);
         } else {
         DCTC16_ITEM_LOOP
         // ===== converters =====
@@ -467,12 +564,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
 }  // namespace
 
 // Returns cudaErrorNotSupported when the configuration is outside this kernel's fast path (the caller then uses the
-// FP32 tile kernel): needs 1 or 3 channels, 16-byte aligned rows, edges == textures, no band-mode / preview request.
+// FP32 tile kernel): needs 1 or 3 channels, 16-byte aligned rows, no band-mode (per-seam) / preview request.
 cudaError_t dctc_launch_k1_tc16(const DctcK1Args& a, int n_frames, bool uniform, int* counter, int sm_count, cudaStream_t stream)
 {
     if (a.w <= 0 || a.h <= 0 || n_frames <= 0) return cudaSuccess;
     auto aligned16 = [](const void* p, size_t pitch) { return (((uintptr_t) p | pitch) & 15) == 0; };
-    const bool fast = uniform && !a.seam && !a.preview && (a.channels == 3 || a.channels == 1) && aligned16(a.img, a.pitch) &&
+    const bool fast = !a.seam && !a.preview && (a.channels == 3 || a.channels == 1) && aligned16(a.img, a.pitch) &&
                       (a.frame_stride & 15) == 0 && (!a.top || aligned16(a.top, a.top_pitch)) && (!a.bot || aligned16(a.bot, a.bot_pitch));
     if (!fast || !counter) return cudaErrorNotSupported;
     const int strips = (a.w + PW - 1) / PW;
@@ -488,7 +585,7 @@ cudaError_t dctc_launch_k1_tc16(const DctcK1Args& a, int n_frames, bool uniform,
     for (int nseg = 1; nseg <= max_segs && nseg <= 64; nseg++) {
         const int sr = even_seg(nseg);
         const long long sg = (rows + sr - 1) / sr, it = (long long) strips * sg * n_frames;
-        const long long per = sr / 16 + 1;
+        const long long per = sr / 16 + 2;   // the two prologue groups of an item cost about two steps
         const long long rounds = (it + ctas - 1) / ctas;
         const long long cost = it <= 8 * ctas ? rounds * per : (it * per + ctas - 1) / ctas + per / 2;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_rows = sr; }
@@ -499,15 +596,14 @@ cudaError_t dctc_launch_k1_tc16(const DctcK1Args& a, int n_frames, bool uniform,
     if (items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int grid = (int) (items < ctas ? items : ctas);
     const int smem = (int) sizeof(Tc16Smem);
-    cudaError_t ea;
-    if (a.channels == 3) {
-        ea = cudaFuncSetAttribute(dctc_k1_tc16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (ea != cudaSuccess) return ea;
-        dctc_k1_tc16_kernel<3><<<grid, NTHREADS, smem, stream>>>(a, seg, strips, segs, (int) items, phase, counter);
-    } else {
-        ea = cudaFuncSetAttribute(dctc_k1_tc16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (ea != cudaSuccess) return ea;
-        dctc_k1_tc16_kernel<1><<<grid, NTHREADS, smem, stream>>>(a, seg, strips, segs, (int) items, phase, counter);
-    }
+#define DCTC16_LAUNCH(U, C)                                                                                            \
+    do {                                                                                                               \
+        cudaError_t ea = cudaFuncSetAttribute(dctc_k1_tc16_kernel<U, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (ea != cudaSuccess) return ea;                                                                              \
+        dctc_k1_tc16_kernel<U, C><<<grid, NTHREADS, smem, stream>>>(a, seg, strips, segs, (int) items, phase, counter); \
+    } while (0)
+    if (a.channels == 3) { if (uniform) DCTC16_LAUNCH(true, 3); else DCTC16_LAUNCH(false, 3); }
+    else { if (uniform) DCTC16_LAUNCH(true, 1); else DCTC16_LAUNCH(false, 1); }
+#undef DCTC16_LAUNCH
     return cudaGetLastError();
 }
