@@ -48,13 +48,15 @@ def kernel_name(blocksize, kernel):
                 2: "dctc_k1_march8_kernel (FP32x2 register march)"}.get(kernel, "dctc_k1_tile_kernel (FP32)")
     if blocksize in (2, 4) and kernel == 0:
         return "dctc_k1_small_kernel (FP32 streaming register march)"
+    if blocksize == 16 and kernel in (0, 3):
+        return "dctc_k1_tc16_kernel (tcgen05 y-pass)"
     return "dctc_k1_tile_kernel (FP32)"
 
 
 def arithmetic(blocksize, kernel):
-    if blocksize == 8 and kernel in (0, 3):
+    if blocksize in (8, 16) and kernel in (0, 3):
         return ("exact integer luma, FP32 x-pass, y-pass on tcgen05 with fp16 hi/lo split operands (22 significant "
-                "bits) and FP32 accumulation; max rel err vs the double reference 1.2e-6")
+                "bits) and FP32 accumulation; max rel err vs the double reference %s" % ("1.2e-6" if blocksize == 8 else "2.5e-6"))
     return "FP32 (max rel err vs the double reference 1e-6)"
 
 
@@ -65,7 +67,8 @@ def kernel_note(blocksize):
                        "see DESIGN.md section 4")
     if blocksize in (2, 4):
         return base + "blocksize %d: HBM / instruction-issue bound streaming kernel, see DESIGN.md section 4" % blocksize
-    return base + "blocksize 16 runs in the FP32 tile kernel (FP32-pipe bound)"
+    return base + ("blocksize 16 is tensor-bound (96 tcgen05 MMAs M128 N128 K16 per 16x64 px: floor ~183 us per 4K frame), "
+                   "not HBM-bound: see DESIGN.md section 4")
 
 
 def shared_config(args, wl):

@@ -33,6 +33,8 @@ struct DctcK1Args {
     // Global row of band row 0 (row bands of a taller image; 0 for whole images).  Only K1-TC16 uses it: its 16-row
     // steps are anchored to the global row grid, so a pixel's FP32 accumulation order does not depend on the band cut.
     int row_origin;
+    // launch with programmatic stream serialization (device seam loop; tile kernel only)
+    int pdl;
 };
 
 // Band limits of row y for a removed seam (seam[] in the coordinates before removal, w = width after removal).

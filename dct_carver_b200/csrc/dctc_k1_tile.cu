@@ -26,6 +26,7 @@
 template <int B, int TW, int TH, int P, bool UNIFORM>
 __global__ void __launch_bounds__(TW* TH / P) dctc_k1_tile_kernel(const DctcK1Args a)
 {
+    DCTC_PDL_PROLOGUE();
     constexpr int NT = TW * TH / P;
     // samples before the pixel: carver path window offsets -B/2+1 .. B/2 (src/render.c:146-147); preview path
     // -(C-1) .. B-C with C = (B-1)/2 (src/render.c:43-44, src/dct.h:8-9)
@@ -149,10 +150,12 @@ static cudaError_t launch_tile(const DctcK1Args& a, int n_frames, bool uniform, 
     if (uniform) {
         e = cudaFuncSetAttribute(dctc_k1_tile_kernel<B, TW, TH, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return e;
+        if (a.pdl) return dctc_launch_pdl(dctc_k1_tile_kernel<B, TW, TH, P, true>, grid, block, smem, stream, true, a);
         dctc_k1_tile_kernel<B, TW, TH, P, true><<<grid, block, smem, stream>>>(a);
     } else {
         e = cudaFuncSetAttribute(dctc_k1_tile_kernel<B, TW, TH, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return e;
+        if (a.pdl) return dctc_launch_pdl(dctc_k1_tile_kernel<B, TW, TH, P, false>, grid, block, smem, stream, true, a);
         dctc_k1_tile_kernel<B, TW, TH, P, false><<<grid, block, smem, stream>>>(a);
     }
     return cudaGetLastError();

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(NT) dctc_carve_rows_kernel(uint8_t* __restrict
                                                              const int* __restrict__ seam, int w_old,
                                                              float* __restrict__ mplane, size_t m_pitch)
 {
+    DCTC_PDL_PROLOGUE();
     const int y = blockIdx.x;
     const int s = seam[y];
     uint8_t* row = img + (size_t) y * pitch;
@@ -264,6 +265,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_MAXW * 32) dc
                                                                     const __grid_constant__ CUtensorMap tmap, int use_tmap,
                                                                     int* __restrict__ xlast)
 {
+    DCTC_PDL_PROLOGUE();
     // fallback of the incremental update (dctc_seam_incr_kernel): runs only when that kernel asked for a rebuild
     if (run_flag && *run_flag == 0) return;       // uniform over the cluster, before any cluster barrier
     if (run_flag && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(run_flag + 1, 1);   // rebuilds since the session was loaded
@@ -612,6 +614,7 @@ constexpr int JB = 32;
 __global__ void __launch_bounds__(128) dctc_seam_jump_kernel(const float* __restrict__ mplane, size_t m_pitch, int w, int h,
                                                              int8_t* __restrict__ jump, size_t j_pitch, int strips)
 {
+    DCTC_PDL_PROLOGUE();
     const int lane = threadIdx.x & 31;
     const int strip = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (strip >= strips) return;
@@ -674,6 +677,7 @@ __global__ void __launch_bounds__(TR_THREADS) dctc_seam_trace_kernel(const float
     extern __shared__ __align__(16) unsigned char tr_smem[];
     __shared__ __align__(16) float win[JB][TR_WIN + 8];
     __shared__ int xb_s;
+    DCTC_PDL_PROLOGUE();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = blockIdx.x;
     const int x0 = *xlast;
@@ -960,6 +964,7 @@ __global__ void __launch_bounds__(32) dctc_seam_incr_kernel(const float* __restr
 __global__ void __launch_bounds__(256) dctc_vs_update_kernel(int* __restrict__ raw, int* __restrict__ vs, int w0,
                                                              const int* __restrict__ seam, int w_old, int order)
 {
+    DCTC_PDL_PROLOGUE();
     const int y = blockIdx.x;
     int* rrow = raw + (size_t) y * w0;
     const int s = seam[y];
@@ -1325,6 +1330,7 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         if (cone_smem > 40 * 1024)
             CK(ctx, cudaFuncSetAttribute(dctc_seam_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cone_smem));
     }
+    const bool pdl = !getenv("DCTC_NO_PDL");
     for (int s = 0; s < n_seams; s++) {
         const int w_old = ctx->c_w;
         int* log_s = ctx->c_seam_log + (size_t) s * h;
@@ -1336,11 +1342,16 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
             ctx->launches++;
         } else {
             // build_mmap, then build_vpath: jump maps of all 32-row blocks in parallel, one trace CTA per block
-            dp<<<DP_CL, wpc * 32, dp_smem, ctx->stream>>>(ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch, ctx->c_seam, log_s, nullptr, nst, tmap, use_tmap, xlast);
+            // (programmatic dependent launches: each kernel of the loop is scheduled while its predecessor drains and
+            // blocks in DCTC_PDL_PROLOGUE until that one's results are visible)
+            CK(ctx, dctc_launch_pdl(dp, dim3(DP_CL), dim3(wpc * 32), dp_smem, ctx->stream, pdl, ctx->c_en, ctx->c_en_pitch, w_old, h, ctx->c_m, m_pitch,
+                                    ctx->c_seam, log_s, (int*) nullptr, nst, tmap, use_tmap, xlast));
             if (par_bt) {
                 const int js = (w_old + 63) / 64;
-                dctc_seam_jump_kernel<<<dim3((js + 3) / 4, nb), 128, 0, ctx->stream>>>(ctx->c_m, m_pitch, w_old, h, ctx->c_dir, j_pitch, js);
-                dctc_seam_trace_kernel<<<nb, TR_THREADS, cone_smem, ctx->stream>>>(ctx->c_m, m_pitch, w_old, h, ctx->c_dir, j_pitch, xlast, ctx->c_seam, log_s);
+                CK(ctx, dctc_launch_pdl(dctc_seam_jump_kernel, dim3((js + 3) / 4, nb), dim3(128), 0, ctx->stream, pdl, ctx->c_m, m_pitch, w_old, h,
+                                        ctx->c_dir, j_pitch, js));
+                CK(ctx, dctc_launch_pdl(dctc_seam_trace_kernel, dim3(nb), dim3(TR_THREADS), cone_smem, ctx->stream, pdl, ctx->c_m, m_pitch, w_old, h,
+                                        ctx->c_dir, j_pitch, xlast, ctx->c_seam, log_s));
                 ctx->launches += 2;
             }
         }
@@ -1348,12 +1359,13 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: dp kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }
 #endif
         if (ctx->c_dump_vmaps) {   // update_vsmap
-            dctc_vs_update_kernel<<<h, 256, 0, ctx->stream>>>(ctx->c_raw, ctx->c_vs, ctx->c_vs_w, ctx->c_seam, w_old, ++ctx->c_vs_depth);
+            CK(ctx, dctc_launch_pdl(dctc_vs_update_kernel, dim3(h), dim3(256), 0, ctx->stream, pdl, ctx->c_raw, ctx->c_vs, ctx->c_vs_w, ctx->c_seam, w_old,
+                                    ++ctx->c_vs_depth));
             ctx->launches++;
         }
         // carve: compact image and energy rows over the seam
-        dctc_carve_rows_kernel<256, 4><<<h, 256, 0, ctx->stream>>>(ctx->c_img, ctx->c_pitch, ctx->c_ch, ctx->c_en,
-                                                                   ctx->c_en_pitch, ctx->c_seam, w_old, incr_ok ? ctx->c_m : nullptr, m_pitch);
+        CK(ctx, dctc_launch_pdl(dctc_carve_rows_kernel<256, 4>, dim3(h), dim3(256), 0, ctx->stream, pdl, ctx->c_img, ctx->c_pitch, ctx->c_ch, ctx->c_en,
+                                ctx->c_en_pitch, ctx->c_seam, w_old, incr_ok ? ctx->c_m : (float*) nullptr, m_pitch));
         CK(ctx, cudaGetLastError());
         ctx->launches += 2;
         ctx->c_w = w_old - 1;
@@ -1362,6 +1374,7 @@ int dctc_carver_resize_width(dctc_context* ctx, int n_seams, int* seams_out)
         DctcK1Args a;
         carver_args(ctx, a);
         a.seam = ctx->c_seam; a.band_r = r; a.band_vals = ctx->c_band_vals; a.band_stride = bs;
+        a.pdl = pdl ? 1 : 0;
 #ifdef DCTC_SYNC_DEBUG
         { cudaError_t e_ = cudaStreamSynchronize(ctx->stream); if (e_ != cudaSuccess) { printf("seam %d: carve kernel failed: %s (w %d)\n", s, cudaGetErrorString(e_), w_old); return dctc_fail_cuda(ctx, e_); } }
 #endif

@@ -7,6 +7,36 @@
 
 struct DctcK1Args;
 
+// Programmatic dependent launch (the kernels of the device seam loop): a kernel launched with the attribute may be
+// scheduled while its predecessor in the stream is still running; its CTAs then block in DCTC_PDL_PROLOGUE until the
+// predecessor has completed and its memory operations are visible.  The macro is a no-op in a normal launch.
+#ifdef DCTC_PDL_NO_EARLY
+#define DCTC_PDL_PROLOGUE() asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+#define DCTC_PDL_PROLOGUE()                                                                                            \
+    do {                                                                                                               \
+        asm volatile("griddepcontrol.launch_dependents;");                                                            \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                                                            \
+    } while (0)
+#endif
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dctc_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                          Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 cudaError_t dctc_launch_k1_tile(const DctcK1Args& a, int blocksize, int n_frames, bool uniform, cudaStream_t stream);
 cudaError_t dctc_launch_k1_small(const DctcK1Args& a, int blocksize, int n_frames, bool uniform, int sm_count, cudaStream_t stream);
 cudaError_t dctc_launch_k1_march8(const DctcK1Args& a, int n_frames, bool uniform, cudaStream_t stream);

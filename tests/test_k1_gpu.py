@@ -255,3 +255,77 @@ def test_full_size_4k_properties(ctx):
     assert np.float64(en2.sum(axis=1, dtype=np.float64)).sum() == np.float64(en.sum(axis=1, dtype=np.float64)).sum()
     ctx.dev_free(d_img)
     ctx.dev_free(d_out)
+
+
+# ---- block size 16 on the tensor cores (dctc_k1_tc16.cu) -------------------------------------------------------------
+
+@pytest.mark.parametrize("wts", [(0.5, 0.5), (0.8, 0.2), (1.0, 0.0)])
+@pytest.mark.parametrize("case", [(0, 3, 64, 16), (0, 3, 208, 150), (0, 1, 144, 67), (3, 3, 96, 130), (3, 3, 640, 300),
+                                  (1, 3, 128, 48), (2, 3, 528, 77), (0, 1, 16, 5), (0, 3, 1, 1), (0, 3, 7, 40)])
+def test_tc16_parity(ctx, wts, case):
+    """Block size 16 through the tcgen05 kernel (16-byte aligned device rows: the host API stages them that way)
+    against the compiled reference / oracle, and within tolerance of the FP32 tile kernel."""
+    pattern, ch, w, h = case
+    img = ol.synth_image(w, h, ch, 1600 + w, pattern)
+    ctx.set_params(16, *wts)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    got = ctx.energy_full(img)
+    ctx.set_kernel(dc.KERNEL_FP32_TILE)
+    tile = ctx.energy_full(img)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    check_with_flips(got, img, 16, *wts)
+    if wts[0] == wts[1]:
+        assert np.abs(got.astype(np.float64) - tile).max() <= 2 * (ol.ABS_TOL + ol.REL_TOL * float(np.abs(tile).max()))
+
+
+@pytest.mark.parametrize("ch,w", [(3, 160), (1, 208)])
+def test_tc16_row_bands_bit_equal_with_band_origin(ctx, ch, w):
+    """dctc_energy_band_dev_at: with the band's image row given, the 16-row accumulation steps of the tensor-core kernel
+    are anchored to the image's row grid, so any cut into bands reproduces the full map BIT for bit (and without the
+    origin it still agrees within the tolerance)."""
+    h = 131
+    img = ol.synth_image(w, h, ch, 1617, 0)
+    ctx.set_params(16, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    full = ctx.energy_full(img)
+    bounds = [(0, 13), (13, 50), (50, 51), (51, 99), (99, 131)]
+    pitch = (w * ch + 15) & ~15
+    buf = np.zeros((h, pitch), np.uint8)
+    buf[:, :w * ch] = img.reshape(h, w * ch)
+    d_img = ctx.dev_alloc(h * pitch)
+    d_out = ctx.dev_alloc(h * w * 4)
+    ctx.h2d(d_img, buf)
+    res = []
+    for with_origin in (True, False):
+        for (y0, y1) in bounds:
+            t, bt = min(7, y0), min(8, h - y1)
+            ctx.energy_band_dev(d_img + y0 * pitch, w, y1 - y0, ch, pitch, d_img + (y0 - t) * pitch if t else None, t, pitch,
+                                d_img + y1 * pitch if bt else None, bt, pitch, d_out + y0 * w * 4, w,
+                                band_y0=y0 if with_origin else 0)
+        out = np.empty((h, w), np.float32)
+        ctx.d2h(out, d_out)
+        res.append(out)
+    ctx.dev_free(d_img)
+    ctx.dev_free(d_out)
+    assert np.array_equal(res[0], full)
+    ol.assert_parity(res[1], ol.best_energy(img, 16, 0.5, 0.5))
+
+
+def test_tc16_persistent_loop_many_items(ctx):
+    """More work items than CTAs (400 small frames in one launch: every CTA re-enters the item loop and re-initialises
+    its barriers), each frame equal to its single-frame launch."""
+    n, w, h, ch = 400, 64, 48, 3
+    imgs = np.stack([ol.synth_image(w, h, ch, 1616, 0, frame=f) for f in range(n)])
+    ctx.set_params(16, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    d_in = ctx.dev_alloc(imgs.nbytes)
+    d_out = ctx.dev_alloc(n * w * h * 4)
+    ctx.h2d(d_in, imgs)
+    ctx.energy_batch_dev(d_in, n, w * h * ch, w, h, ch, w * ch, d_out, w * h, w, sync=True)
+    got = np.empty((n, h, w), np.float32)
+    ctx.d2h(got, d_out)
+    ctx.dev_free(d_in)
+    ctx.dev_free(d_out)
+    for f in (0, 1, 147, 148, 149, 295, 296, 399):
+        assert np.array_equal(got[f], ctx.energy_full(imgs[f])), f
+    ol.assert_parity(got[399], ol.best_energy(imgs[399], 16, 0.5, 0.5))
