@@ -16,6 +16,9 @@
 //       rows i..i+7 of the 16 staged rows), as three kind::f16 MMAs with FP32 accumulation in TMEM:
 //       hi*Bh + lo*Bh + hi*Bl (the dropped lo*Bl term is 2^-22 relative).  Odd steps use the K-swapped copy of Tz
 //       because the older group then sits in ring slot 1.
+//       The basis is stored times 2*sqrt(2) (dctc_tc_tables.cuh): its rows k2 = 0 and 4 are then +-1 exactly, their Bl
+//       term is zero, and the accumulator columns are ordered [k2 = 1,2,3,5,6,7,0,4][row] so that the hi*Bl MMA only
+//       covers the first 48 columns (N = 48).
 //   consumer warps 4-7 (thread = column): tcgen05.ld the 64 accumulators of (8 rows x 8 k2), fold |.|-max over k2
 //       and k1 with FMNMX3 (or the last-arg-max class tracker when edges != textures), scale, coalesced store.
 //
@@ -227,7 +230,12 @@ struct StageMap {
 // 2^22, so its float is exact too); grey is 10000 * v.  Two dp2a per pixel (16-bit coefficients times the pixel's bytes)
 // replace three byte->float conversions and an FMA chain.  The factor 2^-13 of the scaled x-pass
 // (fp16 range of the hi/lo operands) and the 1/10000 are folded into the final weight.
-constexpr float LUMA_WEIGHT_SCALE = 8192.0f / 10000.0f;
+// ... and so is the factor 2*sqrt(2) the stored DCT basis carries (dctc_tc_tables.cuh).
+constexpr float LUMA_WEIGHT_SCALE = (float) (8192.0 / 10000.0 / 2.8284271247461903);
+// accumulator column of (output row i, coefficient k2): the two k2 whose basis rows are exact in fp16 come last
+__host__ __device__ constexpr int tc_cls(int k2) { return k2 == 0 ? 6 : k2 == 4 ? 7 : k2 < 4 ? k2 - 1 : k2 - 2; }
+__host__ __device__ constexpr int tc_k2(int cls) { return cls == 6 ? 0 : cls == 7 ? 4 : cls < 3 ? cls + 1 : cls + 2; }
+__host__ __device__ constexpr int tc_col(int i, int k2) { return tc_cls(k2) * 8 + i; }
 
 template <int CH>
 __device__ __forceinline__ float luma_raw(const uint8_t* __restrict__ p)
@@ -408,11 +416,11 @@ struct TcFold<true> {   // edges == textures: only the maximum matters
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             float t = m[i];
-            if (K1 != 0) t = fmaxf(t, fabsf(__uint_as_float(v[i * 8])));   // (0,0) is skipped (src/dct.c:101)
-            t = fmaxf(t, fabsf(__uint_as_float(v[i * 8 + 1])));
+            if (K1 != 0) t = fmaxf(t, fabsf(__uint_as_float(v[tc_col(i, 0)])));   // (0,0) is skipped (src/dct.c:101)
+            t = fmaxf(t, fabsf(__uint_as_float(v[tc_col(i, 1)])));
 #pragma unroll
             for (int k2 = 2; k2 < 8; k2 += 2)
-                t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[i * 8 + k2])), fabsf(__uint_as_float(v[i * 8 + k2 + 1]))));
+                t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[tc_col(i, k2)])), fabsf(__uint_as_float(v[tc_col(i, k2 + 1)]))));
             m[i] = t;
         }
     }
@@ -444,17 +452,17 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             if (K1 == 0) {
-                const float a = fabsf(__uint_as_float(v[i * 8 + 1]));
+                const float a = fabsf(__uint_as_float(v[tc_col(i, 1)]));
                 float mm = -1.0f;
 #pragma unroll
-                for (int k2 = 2; k2 < 8; k2++) mm = fmaxf(mm, fabsf(__uint_as_float(v[i * 8 + k2])));
+                for (int k2 = 2; k2 < 8; k2++) mm = fmaxf(mm, fabsf(__uint_as_float(v[tc_col(i, k2)])));
                 park[i * MW] = fmaxf(a, mm);
                 if (mm >= a) flags |= 1u << i;
             } else {
-                if (K1 == 1) park[(8 + i) * MW] = fabsf(__uint_as_float(v[i * 8]));
-                else z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[i * 8])));
+                if (K1 == 1) park[(8 + i) * MW] = fabsf(__uint_as_float(v[tc_col(i, 0)]));
+                else z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[tc_col(i, 0)])));
 #pragma unroll
-                for (int k2 = 1; k2 < 8; k2++) z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[i * 8 + k2])));
+                for (int k2 = 1; k2 < 8; k2++) z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[tc_col(i, k2)])));
             }
         }
     }
@@ -504,12 +512,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // Toeplitz operands: Tz[n = i*8 + k2][k] = B8[k2][r - i] with window row r = k (normal) or k ^ 8 (K-swapped)
+    // Toeplitz operands: Tz[n = tc_col(i, k2)][k] = B8[k2][r - i] with window row r = k (normal) or k ^ 8 (K-swapped)
     {
         uint16_t* Bq = reinterpret_cast<uint16_t*>(&s.B[0][0]);
         for (int idx = tid; idx < 4 * 1024; idx += NTHREADS) {
             const int v = idx >> 10, n = (idx >> 4) & 63, k = idx & 15;
-            const int i = n >> 3, k2 = n & 7;
+            const int i = n & 7, k2 = tc_k2(n >> 3);
             const int c = ((v & 2) ? (k ^ 8) : k) - i;
             const uint16_t val = (c >= 0 && c < 8) ? DCTC_TC_BASIS8[v & 1][k2 * 8 + c] : (uint16_t) 0;
             Bq[v * 1024 + (n >> 3) * 128 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7)] = val;
@@ -623,6 +631,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         DCTC_ITEM_LOOP
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc(128, 64);
+        const uint32_t idesc_bl = make_idesc(128, 48);           // hi*Bl: the columns of k2 = 0, 4 (Bl = 0) are skipped
         const uint64_t bd0 = make_smem_desc(smem_u32(&s.B[0][0]), 128, 256);
         for (int st = 0; st < nsteps; st++) {
             {
@@ -649,7 +658,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
                     const uint32_t ah = tmem + TM_A + (uint32_t) k1 * 16u, al = ah + 8u;
                     mma_ts(d, ah, bh, idesc, 0u);
                     mma_ts(d, al, bh, idesc | (1u << 13), 1u);   // A negated: the ring holds -lo
-                    mma_ts(d, ah, bl, idesc, 1u);
+                    mma_ts(d, ah, bl, idesc_bl, 1u);
                     mma_commit(smem_u32(&s.bar_d_full[b]));
                     if (k1 == 3 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free_lo));
                     if (k1 == 7 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free));   // waited on by the producers of group st+2
