@@ -14,7 +14,9 @@
 // column l & 63, m = 0..7 -- a DCT-16 splits into an even half (sums v[j] + v[15-j]) and an odd half (differences)
 // with no shared work, so nothing is computed twice and the operands of a step fill exactly half of TMEM:
 //     A ring  256 columns: [m][hi|lo][slot g&1][row pair]   (8 columns = 16 rows = one K = 16 operand)
-//     D tiles 2 x 128 columns: tile h holds k2 = 8h .. 8h+7 of the 16 output rows, column n = i*8 + (k2 & 7)
+//     D tiles 2 x 128 columns: tile h holds k2 = 8h .. 8h+7 of the 16 output rows, column n = tc16_col(i, k2 & 7):
+//       ordered [k2 & 7 = 1..7, 0][row], because the basis rows k2 = 0 and 8 (all entries +-1/4) are exact in fp16, their
+//       Bl term is zero and the hi*Bl MMAs only cover the first 112 columns
 // Per (step, m): 2 tiles x 2 groups x 3 split terms = 12 MMAs M128 N128 K16 (68.3 clk each): 6560 clk per 1024 px,
 // i.e. a tensor floor of ~183 us per 4K frame -- and, unlike block size 8, everything else (x-pass 60, split 32, fold
 // 128 FMNMX3 per pixel) fits in that shadow, so the roles are built for slack, not for instruction count:
@@ -60,6 +62,8 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_A = 0;       // (m*2 + part)*16 + slot*8 + pair
 constexpr uint32_t TM_D = 256;     // two accumulator tiles of 128 columns
 constexpr float LUMA_WEIGHT_SCALE = 8192.0f / 10000.0f;
+// accumulator column of (output row i, k2 & 7): the k2 whose basis row is exact in fp16 (k2 & 7 == 0) comes last
+__host__ __device__ constexpr int tc16_col(int i, int k2l) { return ((k2l + 7) & 7) * 16 + i; }
 
 struct alignas(128) Tc16Smem {
     __half B[8][2048];               // Tz sub-operands [(v*2 + kh)*2 + h]: v = Bh/Bl, kh = K half (group), h = k2 half (tile)
@@ -299,11 +303,11 @@ __device__ __forceinline__ void fold_tile(const uint32_t (&v)[128], float (&mx)[
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         float t = mx[i];
-        if (DC) t = fmaxf(t, fabsf(__uint_as_float(v[i * 8 + 1])));
-        else t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[i * 8])), fabsf(__uint_as_float(v[i * 8 + 1]))));
+        if (DC) t = fmaxf(t, fabsf(__uint_as_float(v[tc16_col(i, 1)])));
+        else t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[tc16_col(i, 0)])), fabsf(__uint_as_float(v[tc16_col(i, 1)]))));
 #pragma unroll
         for (int k = 2; k < 8; k += 2)
-            t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[i * 8 + k])), fabsf(__uint_as_float(v[i * 8 + k + 1]))));
+            t = fmaxf(t, fmaxf(fabsf(__uint_as_float(v[tc16_col(i, k)])), fabsf(__uint_as_float(v[tc16_col(i, k + 1)]))));
         mx[i] = t;
     }
 }
@@ -321,7 +325,7 @@ __device__ __forceinline__ void fold_tile_class(const uint32_t (&v)[128], float 
     for (int i = 0; i < 16; i++) {
         float f[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) f[k] = fabsf(__uint_as_float(v[i * 8 + k]));
+        for (int k = 0; k < 8; k++) f[k] = fabsf(__uint_as_float(v[tc16_col(i, k)]));
         const float m27 = fmaxf(fmaxf(f[2], fmaxf(f[3], f[4])), fmaxf(f[5], fmaxf(f[6], f[7])));
         if (KIND == 0) {
             cb[4][i][px] = f[1];
@@ -348,14 +352,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // Toeplitz sub-operands as UMMA K-major no-swizzle tiles: element (n = i*8 + k2l, k) of sub-operand (v, kh, h) is
+    // Toeplitz sub-operands as UMMA K-major no-swizzle tiles: element (n = tc16_col(i, k2l), k) of sub-operand (v, kh, h) is
     // B16[8h + k2l][16 kh + k - i] (zero outside the basis)
     {
         uint16_t* Bq = reinterpret_cast<uint16_t*>(&s.B[0][0]);
         for (int idx = tid; idx < 8 * 2048; idx += NTHREADS) {
             const int sub = idx >> 11, n = (idx >> 4) & 127, k = idx & 15;
             const int v = sub >> 2, kh = (sub >> 1) & 1, h = sub & 1;
-            const int i = n >> 3, k2 = 8 * h + (n & 7);
+            const int i = n & 15, k2 = 8 * h + (((n >> 4) + 1) & 7);
             const int c = 16 * kh + k - i;
             const uint16_t val = (c >= 0 && c < 16) ? DCTC_TC_BASIS16[v][k2 * 16 + c] : (uint16_t) 0;
             Bq[sub * 2048 + (n >> 3) * 128 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7)] = val;
@@ -500,6 +504,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
         DCTC16_ITEM_LOOP
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc(128, 128);
+        const uint32_t idesc_bl = make_idesc(128, 112);          // hi*Bl: the columns of k2 & 7 == 0 (Bl = 0) are skipped
         const uint64_t bd0 = make_smem_desc(smem_u32(&s.B[0][0]), 128, 256);   // sub-operand stride: 4096 B = 256 address units
         for (int st = 0; st < nsteps; st++) {
             const uint32_t so = (uint32_t) (st & 1) * 8u, sn = so ^ 8u;   // ring slots of the older / newer group
@@ -522,10 +527,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
                         const uint64_t bl0 = bd0 + (uint64_t) (256 * ((1 * 2 + 0) * 2 + h)), bl1 = bd0 + (uint64_t) (256 * ((1 * 2 + 1) * 2 + h));
                         mma_ts(d, ah + so, bh0, idesc, 0u);
                         mma_ts(d, al + so, bh0, idesc | (1u << 13), 1u);   // A negated: the ring holds -lo
-                        mma_ts(d, ah + so, bl0, idesc, 1u);
+                        mma_ts(d, ah + so, bl0, idesc_bl, 1u);
                         mma_ts(d, ah + sn, bh1, idesc, 1u);
                         mma_ts(d, al + sn, bh1, idesc | (1u << 13), 1u);
-                        mma_ts(d, ah + sn, bl1, idesc, 1u);
+                        mma_ts(d, ah + sn, bl1, idesc_bl, 1u);
                         mma_commit(smem_u32(&s.bar_d_full[h]));
                         if (h == 1 && st + 2 <= nsteps) mma_commit(smem_u32(&s.bar_a_free[m]));   // waited on by the producers of group st+2
                     }
