@@ -4,7 +4,10 @@
 // ddct8x8s, src/fft2d/shrtdct.c:61-117).  A CTA owns a strip of 128 columns and marches down its segment 8 rows
 // ("a group") at a time; pixel column x0+m is row m of every MMA (TMEM lane m).
 //
-//   converter warps 9-10: cp.async the raw rows two groups ahead (triple-buffered), convert one group to luma
+//   converter warps 9-11: stage the raw rows two groups ahead (triple-buffered): the 8 x 416-byte tile of a group that
+//       lies inside the image is ONE 3-D tensor copy (TMA, cp.async.bulk.tensor.3d over (row bytes / 4, rows, frames),
+//       completion on the buffer's mbarrier); groups that touch the top / bottom edge or the halo rows of a band (edge
+//       replication, src/render.c:122-132) are gathered row by row with 16-byte cp.async.  Then convert one group to luma
 //       (four pixels x two rows per task: 32-bit shared loads, PRMT + FADD byte->float, no XU-pipe conversions) and
 //       hand the luma row pairs to the producers through hardware named barriers (double-buffered)
 //   producer warps 0-3 (thread = column): run the
@@ -24,8 +27,10 @@
 //
 // Per pixel the CUDA cores execute ~100 instructions instead of the ~264 of the FP32 march kernel; the tensor pipe
 // does 24 M128 N64 K16 MMAs per 1024 pixels (36.3 clk each measured, profiles/r01_tcgen05_probe2.txt).
+#include <cuda.h>       // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_fp16.h>
 #include <cstdio>
+#include <cstring>
 #include "dctc_common.cuh"
 #include "dctc_launch.h"
 #include "dctc_tc_tables.cuh"
@@ -69,6 +74,7 @@ struct alignas(128) TcSmem {
     uint8_t Raw[3][8 * RawGeom<3>::ROW];
     float park[16][MW];              // non-uniform weights: per-row quantities of the class rule parked by the consumers
     uint64_t bar_a_free, bar_a_free_lo, bar_d_full[2];
+    uint64_t bar_raw[3];             // raw buffer filled: NCONV arrivals (+ the bytes of a tensor copy)
     uint32_t tmem_base;
     int work;
 };
@@ -181,47 +187,46 @@ __device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t (&v)[64])
 }
 
 // ---- staging + conversion (converter warps) ----------------------------------------------------------------------
-// The raw interleaved bytes [x0*CH-16, x0*CH+(MW+4)*CH) of the 8 rows of a group are copied global -> shared with
-// 16-byte cp.async two groups ahead of their conversion (x0*CH is 16-byte aligned: x0 is a multiple of 128).
-// Chunks outside [0, pitch) are skipped: clamped pixel indices never read them.
-// The chunk -> (row, byte offset) mapping of a converter thread is the same for every group of an item: it is computed
-// once (StageMap) and a group costs one row-pointer lookup and one cp.async per chunk.
+// The raw interleaved bytes [x0*CH-16, x0*CH-16+ROW) of the 8 rows of a group are staged global -> shared two groups ahead
+// of their conversion (x0*CH is 16-byte aligned: x0 is a multiple of 128).  Every converter thread arrives once per group
+// on the raw buffer's mbarrier:
+//   * group inside the image (no halo rows, no edge replication): thread 0 issues one 3-D tensor copy (box = ROW/4 x 8 x 1
+//     32-bit elements at (x0*CH/4 - 4, vy0, frame); bytes left of the row start / beyond the pitch are zero-filled and
+//     never read) and arrives with the expected byte count, the others just arrive;
+//   * otherwise each thread gathers its 16-byte chunks with cp.async from the clamped / halo row pointers (chunks
+//     outside [0, pitch) are skipped) and arrives through cp.async.mbarrier.arrive.noinc.
 template <int CH>
 struct StageMap {
     static constexpr int CHUNKS = RawGeom<CH>::CHUNKS;
     static constexpr int PER = (8 * CHUNKS + NCONV - 1) / NCONV;   // chunks per thread (CH=3: 3, CH=1: 1)
-    int ly[PER];               // row of the group, -1: no copy
-    int soff[PER];             // byte offset inside a raw buffer
-    const uint8_t* src[PER];   // source of the chunk in the group staged last
-    int last_vy0;              // first virtual row of that group; INT_MIN: none yet
-    __device__ __forceinline__ void init(const DctcK1Args& a, int x0, int ct)
+    __device__ __forceinline__ static void gather(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R, int vy0, int x0, int ct)
     {
 #pragma unroll
         for (int i = 0; i < PER; i++) {
             const int c = ct + i * NCONV;
             const int r = c / CHUNKS, k = c - r * CHUNKS;
             const long long gb = (long long) x0 * CH - 16 + 16 * k;
-            soff[i] = r * RawGeom<CH>::ROW + 16 * k;
-            ly[i] = (c < 8 * CHUNKS && gb >= 0 && gb + 16 <= (long long) a.pitch) ? r : -1;
-            src[i] = nullptr;
-        }
-        last_vy0 = (int) 0x80000000;
-    }
-    // Groups advance by 8 rows: while a group and its predecessor lie inside the band itself (no halo rows, no edge
-    // replication) the source pointers just move by 8 pitches; otherwise they are looked up row by row.
-    __device__ __forceinline__ void stage(const DctcK1Args& a, const uint8_t* __restrict__ img, uint8_t* __restrict__ R, int vy0, int x0)
-    {
-        const bool step8 = vy0 == last_vy0 + 8 && last_vy0 >= 0 && vy0 + 7 < a.h;
-#pragma unroll
-        for (int i = 0; i < PER; i++) {
-            if (ly[i] >= 0) {
-                if (step8) src[i] += 8 * a.pitch;
-                else src[i] = dctc_row_ptr(a, img, vy0 + ly[i]) + ((long long) x0 * CH - 16 + (soff[i] - ly[i] * RawGeom<CH>::ROW));
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(R + soff[i])), "l"(src[i]) : "memory");
+            if (c < 8 * CHUNKS && gb >= 0 && gb + 16 <= (long long) a.pitch) {
+                const uint8_t* src = dctc_row_ptr(a, img, vy0 + r) + gb;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(R + r * RawGeom<CH>::ROW + 16 * k)), "l"(src) : "memory");
             }
         }
-        last_vy0 = vy0;
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ static void stage(const DctcK1Args& a, const CUtensorMap* tmap, int use_tmap, const uint8_t* __restrict__ img,
+                                                 int frame, uint8_t* __restrict__ R, uint32_t bar, int vy0, int x0, int ct)
+    {
+        if (use_tmap && vy0 >= 0 && vy0 + 7 < a.h) {
+            if (ct == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (8 * RawGeom<CH>::ROW)) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(smem_u32(R)), "l"(tmap), "r"(x0 * CH / 4 - 4), "r"(vy0), "r"(frame), "r"(bar) : "memory");
+            } else {
+                mbar_arrive(bar);
+            }
+        } else {
+            gather(a, img, R, vy0, x0, ct);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+        }
     }
 };
 
@@ -502,7 +507,8 @@ __device__ __forceinline__ void consume_k1(TcSmem& s, TcFold<UNIFORM>& f, uint32
 // atomic counter.
 template <bool UNIFORM, int CH>
 __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Args a, int seg_rows, int strips, int segs, int n_items,
-                                                                    int* __restrict__ counter)
+                                                                    int* __restrict__ counter, const __grid_constant__ CUtensorMap tmap,
+                                                                    int use_tmap)
 {
     __shared__ TcSmem s;
     const int tid = threadIdx.x;
@@ -540,11 +546,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
                 mbar_inval(smem_u32(&s.bar_a_free_lo));
                 mbar_inval(smem_u32(&s.bar_d_full[0]));
                 mbar_inval(smem_u32(&s.bar_d_full[1]));
+                for (int i = 0; i < 3; i++) mbar_inval(smem_u32(&s.bar_raw[i]));
             }
             mbar_init(smem_u32(&s.bar_a_free), 1);
             mbar_init(smem_u32(&s.bar_a_free_lo), 1);
             mbar_init(smem_u32(&s.bar_d_full[0]), 1);
             mbar_init(smem_u32(&s.bar_d_full[1]), 1);
+            for (int i = 0; i < 3; i++) mbar_init(smem_u32(&s.bar_raw[i]), NCONV);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         tc_fence_before();
@@ -565,6 +573,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         const int strip = item % strips;                                                                               \
         const int rest = item / strips;                                                                                \
         const int seg = rest % segs, frame = rest / segs;                                                              \
+        (void) frame;                                                                                                  \
         const int x0 = strip * MW;                                                                                     \
         const int y0 = seg * seg_rows;                                                                                 \
         const int y1 = min(y0 + seg_rows, a.h);                                                                        \
@@ -677,22 +686,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         DCTC_ITEM_LOOP
         // ===== converters: raw rows of group g+2 in flight while group g is converted =====
         const int ct = tid - (NTHREADS - NCONV);
-        StageMap<CH> sm;
-        sm.init(a, x0, ct);
         ConvMap<CH> cm;
         cm.init(a, x0, ct);
-        sm.stage(a, img, s.Raw[0], y0 - 3, x0);
-        sm.stage(a, img, s.Raw[1], y0 + 5, x0);
+        StageMap<CH>::stage(a, &tmap, use_tmap, img, frame, s.Raw[0], smem_u32(&s.bar_raw[0]), y0 - 3, x0, ct);
+        StageMap<CH>::stage(a, &tmap, use_tmap, img, frame, s.Raw[1], smem_u32(&s.bar_raw[1]), y0 + 5, x0, ct);
         int slot = 0;                                         // raw buffer of group g (g % 3)
+        uint32_t par = 0u;                                    // bit i: parity of the next completion of raw buffer i
         for (int g = 0; g <= nsteps; g++) {
             {
                 TT_T0();
-                asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of group g have landed
+                mbar_wait(smem_u32(&s.bar_raw[slot]), (par >> slot) & 1u);   // the copies of group g have landed
+                par ^= 1u << slot;
                 TT_ACC(3, 0);
             }
             {
                 TT_T0();
-                bar_converters();                             // ... everybody's; raw buffer (g+2)%3 = (g-1)%3 is free
+                bar_converters();                             // every converter has left group g-1: raw buffer (g+2)%3 = (g-1)%3 is free
                 TT_ACC(3, 1);
             }
             if (g >= 2) {
@@ -703,8 +712,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
             cm.convert(a, s.Raw[slot], &s.L[g & 1][0][0]);
             bar_lfull_arrive(g & 1);
             const int nslot = slot == 0 ? 2 : slot - 1;       // (g + 2) % 3
-            if (g + 2 <= nsteps) sm.stage(a, img, s.Raw[nslot], y0 - 3 + 8 * (g + 2), x0);
-            else asm volatile("cp.async.commit_group;" ::: "memory");
+            if (g + 2 <= nsteps)
+                StageMap<CH>::stage(a, &tmap, use_tmap, img, frame, s.Raw[nslot], smem_u32(&s.bar_raw[nslot]), y0 - 3 + 8 * (g + 2), x0, ct);
             slot = slot == 2 ? 0 : slot + 1;
         }
         // the last two groups' "free" arrivals were never waited for: drain them so the next item starts clean
@@ -770,11 +779,44 @@ cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, 
     const long long items = (long long) strips * segs * n_frames;
     if (items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int grid = (int) (items < 2LL * sm_count ? items : 2LL * sm_count);
+    // tensor map of the frames as 32-bit elements: (pitch / 4, h, frames); box = one staged raw tile (ROW / 4 x 8 x 1)
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int use_tmap = 0;
+    {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static encode_fn encode = nullptr;
+        static bool looked = false;
+        if (!looked) {
+            void* fp = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) == cudaSuccess && fp &&
+                qres == cudaDriverEntryPointSuccess)
+                encode = (encode_fn) fp;
+            else
+                (void) cudaGetLastError();
+            looked = true;
+        }
+        const size_t fstride = n_frames > 1 ? a.frame_stride : a.pitch * (size_t) a.h;
+        const int row = a.channels == 3 ? RawGeom<3>::ROW : RawGeom<1>::ROW;
+        if (encode && a.h >= 8 && !getenv("DCTC_TC_NO_TENSORMAP") && (fstride & 15) == 0 && fstride >= a.pitch && a.pitch < (1ull << 40) &&
+            fstride < (1ull << 40)) {
+            const cuuint64_t gdim[3] = {(cuuint64_t) (a.pitch / 4), (cuuint64_t) a.h, (cuuint64_t) n_frames};
+            const cuuint64_t gstr[2] = {(cuuint64_t) a.pitch, (cuuint64_t) fstride};
+            const cuuint32_t box[3] = {(cuuint32_t) (row / 4), 8u, 1u};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(a.img), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                use_tmap = 1;
+        }
+    }
 #define DCTC_TC_LAUNCH(U, C)                                                                                           \
     do {                                                                                                               \
         cudaError_t ea = cudaFuncSetAttribute(dctc_k1_tc8_kernel<U, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAD_SMEM); \
         if (ea != cudaSuccess) return ea;                                                                              \
-        dctc_k1_tc8_kernel<U, C><<<grid, NTHREADS, PAD_SMEM, stream>>>(a, seg, strips, segs, (int) items, counter);    \
+        dctc_k1_tc8_kernel<U, C><<<grid, NTHREADS, PAD_SMEM, stream>>>(a, seg, strips, segs, (int) items, counter, tmap, use_tmap); \
     } while (0)
     if (a.channels == 3) { if (uniform) DCTC_TC_LAUNCH(true, 3); else DCTC_TC_LAUNCH(false, 3); }
     else { if (uniform) DCTC_TC_LAUNCH(true, 1); else DCTC_TC_LAUNCH(false, 1); }
