@@ -605,6 +605,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         const int px = tid - 128;
         const int gx = x0 + px;
         const bool lane0 = (tid & 31) == 0;
+        // one running output pointer per item (advanced by 8 rows per step) instead of a 64-bit row address per store
+        const size_t op = a.out_pitch;
+        float* __restrict__ orow = out + (size_t) y0 * op + gx;
+        const float we = a.w_edges * LUMA_WEIGHT_SCALE, wt = a.w_textures * LUMA_WEIGHT_SCALE;
         for (int st = 0; st < nsteps; st++) {
             TcFold<UNIFORM> f;
             f.init();
@@ -620,16 +624,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
             consume_k1<7, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
             const int gy = y0 + 8 * st;
             if (gx < a.w) {
-                float* __restrict__ o = out + (size_t) gy * a.out_pitch + gx;
+                float* __restrict__ o = orow;
                 if (gy + 8 <= y1) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) o[(size_t) i * a.out_pitch] = f.result(i, a.w_edges * LUMA_WEIGHT_SCALE, a.w_textures * LUMA_WEIGHT_SCALE);
+                    for (int i = 0; i < 8; i++) { *o = f.result(i, we, wt); o += op; }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if (gy + i < y1) o[(size_t) i * a.out_pitch] = f.result(i, a.w_edges * LUMA_WEIGHT_SCALE, a.w_textures * LUMA_WEIGHT_SCALE);
+                    for (int i = 0; i < 8; i++) {
+                        if (gy + i < y1) *o = f.result(i, we, wt);
+                        o += op;
+                    }
                 }
             }
+            orow += 8 * op;
         }
         end_item();
         }
