@@ -134,8 +134,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // group stored (producers -> MMA warp).  A blocked bar.sync costs no issue slots, unlike an mbarrier poll loop.
 __device__ __forceinline__ void bar_step_arrive() { asm volatile("bar.arrive 9, 160;" ::: "memory"); }
 __device__ __forceinline__ void bar_step_sync() { asm volatile("bar.sync 9, 160;" ::: "memory"); }
-__device__ __forceinline__ void bar_afull_arrive() { asm volatile("bar.arrive 10, 160;" ::: "memory"); }
-__device__ __forceinline__ void bar_afull_sync() { asm volatile("bar.sync 10, 160;" ::: "memory"); }
+// "operands stored" comes in two halves (k1 = 0..3 -> barrier 10, k1 = 4..7 -> barrier 11): the first four tiles of a step
+// start while the producers still store the second half behind the previous step's last MMAs
+__device__ __forceinline__ void bar_afull_arrive(int half) { asm volatile("bar.arrive %0, 160;" ::"r"(10 + half) : "memory"); }
+__device__ __forceinline__ void bar_afull_sync(int half) { asm volatile("bar.sync %0, 160;" ::"r"(10 + half) : "memory"); }
 __device__ __forceinline__ void bar_converters() { asm volatile("bar.sync 4, 96;" ::: "memory"); }
 __device__ __forceinline__ void bar_lfull_arrive(int b) { asm volatile("bar.arrive %0, 224;" ::"r"(5 + b) : "memory"); }
 __device__ __forceinline__ void bar_lfull_sync(int b) { asm volatile("bar.sync %0, 224;" ::"r"(5 + b) : "memory"); }
@@ -390,17 +392,17 @@ __device__ __forceinline__ void produce_group(TcSmem& s, int g, int tid, uint32_
             tmem_st_x4(ta + (uint32_t) (k1 * 16), hi[k1][0], hi[k1][1], hi[k1][2], hi[k1][3]);
             tmem_st_x4(ta + (uint32_t) (k1 * 16 + 8), lo[k1][0], lo[k1][1], lo[k1][2], lo[k1][3]);
         }
+        {
+            TT_T0();
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // warp-wide: every lane's stores have completed
+            TT_ACC(0, 2);
+        }
+        tc_fence_before();
+        // Group 0 is not announced on its own: the arrivals of group 1 cover both (same warp, program order).  The
+        // arrival of half hk of group g+1 needs the completion of the MMAs k1 <= 4 hk + 3 of step g-1, which the MMA warp
+        // issues after its sync on this half for step g-1: there is never more than one pending arrival per barrier.
+        if (g >= 1) bar_afull_arrive(hk);
     }
-    {
-        TT_T0();
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // warp-wide: every lane's stores have completed
-        TT_ACC(0, 2);
-    }
-    tc_fence_before();
-    // Group 0 is not announced on its own: the arrival of group 1 covers both (same warp, program order).  The arrival
-    // of group g+1 needs the completion of MMA step g-1, which the MMA warp issues after its sync for step g-1: there
-    // is never more than one pending arrival.
-    if (g >= 1) bar_afull_arrive();
 }
 
 // ---- consumer fold -------------------------------------------------------------------------------------------
@@ -652,7 +654,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         for (int st = 0; st < nsteps; st++) {
             {
                 TT_T0();
-                bar_afull_sync();                             // groups st and st+1 are in TMEM
+                bar_afull_sync(0);                            // the k1 = 0..3 operands of groups st and st+1 are in TMEM
                 TT_ACC(2, 0);
             }
             tc_fence_after();
@@ -663,6 +665,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
 #pragma unroll
             for (int k1 = 0; k1 < 8; k1++) {
                 const int b = k1 & 1;
+                if (k1 == 4) {
+                    bar_afull_sync(1);                        // ... and the k1 = 4..7 operands
+                    tc_fence_after();
+                }
                 if (st > 0 || k1 >= 2) {
                     TT_T0();
                     bar_tile_sync(b);                         // the consumers have loaded the previous contents of tile b
