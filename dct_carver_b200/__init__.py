@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("DCTC_LIB") or os.path.join(_HERE, "libdctc.so")   # D
 
 OK = 0
 ERR_INVALID, ERR_BLOCKSIZE, ERR_NOMEM, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
-KERNEL_AUTO, KERNEL_FP32_TILE, KERNEL_FP32_MARCH, KERNEL_TC_SPLIT = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_FP32_TILE, KERNEL_FP32_MARCH, KERNEL_TC_SPLIT, KERNEL_FP32_STREAM = 0, 1, 2, 3, 4
 
 # every symbol include/dctc.h declares (tests check that the library exports exactly these)
 ABI_SYMBOLS = [

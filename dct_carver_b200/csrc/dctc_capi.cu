@@ -137,7 +137,7 @@ int dctc_set_params(dctc_context* ctx, const DctcEnergyParameters* p)
 int dctc_set_kernel(dctc_context* ctx, int kernel)
 {
     if (!ctx) return DCTC_ERR_INVALID;
-    if (kernel < DCTC_KERNEL_AUTO || kernel > DCTC_KERNEL_TC_SPLIT) return DCTC_ERR_INVALID;
+    if (kernel < DCTC_KERNEL_AUTO || kernel > DCTC_KERNEL_FP32_STREAM) return DCTC_ERR_INVALID;
     ctx->kernel = kernel;
     return DCTC_OK;
 }
@@ -165,9 +165,11 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
     // band mode (per-seam update) always runs in the tile kernel; block size 8 full maps default to the tensor-core
     // kernel (which hands configurations outside its fast path to the FP32 march kernel)
     if (a.seam || ctx->blocksize != 8) {
-        kernel = DCTC_KERNEL_FP32_TILE;   // the kernel choice (dctc_set_kernel) only concerns block size 8 full maps
+        kernel = DCTC_KERNEL_FP32_TILE;   // block sizes 2, 4, 16 pick their fast path below
     } else if (kernel == DCTC_KERNEL_AUTO) {
         kernel = DCTC_KERNEL_TC_SPLIT;
+    } else if (kernel == DCTC_KERNEL_FP32_STREAM) {
+        kernel = DCTC_KERNEL_FP32_MARCH;  // block size 8 has no streaming kernel: its register-march kernel
     }
     cudaError_t e;
     switch (kernel) {
@@ -175,7 +177,11 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
         // block sizes 2 and 4 (HBM-bound): full maps stream through the register-march kernel unless the tile kernel was
         // asked for explicitly; both produce bit-identical maps
         e = cudaErrorNotSupported;
-        if (ctx->kernel == DCTC_KERNEL_AUTO && !a.seam && !a.preview && (ctx->blocksize == 2 || ctx->blocksize == 4))
+        // block size 4 (FP32-pipe-bound on the CUDA cores): full maps run their y-pass on the tensor cores
+        if ((ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_TC_SPLIT) && !a.seam && !a.preview && ctx->blocksize == 4)
+            e = dctc_launch_k1_tc4(a, n_frames, uniform, ctx->tc_counters + (ctx->tc_next++ % DCTC_TC_COUNTERS), ctx->sm_count, stream);
+        if (e == cudaErrorNotSupported && (ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_FP32_STREAM) && !a.seam && !a.preview &&
+            (ctx->blocksize == 2 || ctx->blocksize == 4))
             e = dctc_launch_k1_small(a, ctx->blocksize, n_frames, uniform, ctx->sm_count, stream);
         // block size 16 (compute-bound): full maps run their y-pass on the tensor cores unless the FP32 tile kernel was
         // asked for explicitly (or the configuration is outside the tensor-core fast path)

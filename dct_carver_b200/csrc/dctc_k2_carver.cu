@@ -1091,7 +1091,7 @@ static int carver_full_energy(dctc_context* ctx)
     DctcK1Args a;
     carver_args(ctx, a);
     const int saved_kernel = ctx->kernel;
-    if (ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_TC_SPLIT) ctx->kernel = DCTC_KERNEL_FP32_MARCH;
+    if (ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_TC_SPLIT || ctx->kernel == DCTC_KERNEL_FP32_STREAM) ctx->kernel = DCTC_KERNEL_FP32_MARCH;
     const int rc = dctc_run_k1(ctx, a, 1, ctx->stream);
     ctx->kernel = saved_kernel;
     return rc;
