@@ -204,6 +204,21 @@ def test_stream_kernel_small_blocks(ctx, b, wts, case):
     check_with_flips(got, img, b, *wts)
 
 
+@pytest.mark.parametrize("b", [2, 4, 8])
+def test_stream_kernel_selector(ctx, b):
+    """dctc_set_kernel(DCTC_KERNEL_FP32_STREAM) names the streaming kernel of block sizes 2 and 4 explicitly (it is also what
+    DCTC_KERNEL_AUTO picks for them); block size 8 has no streaming kernel and takes its FP32 register-march kernel."""
+    img = ol.synth_image(272, 37, 3, 99 + b, 0)
+    ctx.set_params(b, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_FP32_STREAM)
+    got = ctx.energy_full(img)
+    ctx.set_kernel(dc.KERNEL_AUTO if b != 8 else dc.KERNEL_FP32_MARCH)
+    want = ctx.energy_full(img)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    ol.assert_parity(got, ol.best_energy(img, b, 0.5, 0.5))
+
+
 @pytest.mark.parametrize("b", [2, 4])
 @pytest.mark.parametrize("ch,w", [(3, 160), (1, 208)])
 def test_row_bands_stream_kernel(ctx, b, ch, w):
