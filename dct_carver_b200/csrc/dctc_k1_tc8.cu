@@ -800,18 +800,16 @@ cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, 
         typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static encode_fn encode = nullptr;
-        static bool looked = false;
-        if (!looked) {
+        // looked up once (thread-safe static initialisation: dctc_multi_* launches from one host thread per device)
+        static const encode_fn encode = []() -> encode_fn {
             void* fp = nullptr;
             cudaDriverEntryPointQueryResult qres;
             if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) == cudaSuccess && fp &&
                 qres == cudaDriverEntryPointSuccess)
-                encode = (encode_fn) fp;
-            else
-                (void) cudaGetLastError();
-            looked = true;
-        }
+                return (encode_fn) fp;
+            (void) cudaGetLastError();
+            return nullptr;
+        }();
         const size_t fstride = n_frames > 1 ? a.frame_stride : a.pitch * (size_t) a.h;
         const int row = a.channels == 3 ? RawGeom<3>::ROW : RawGeom<1>::ROW;
         if (encode && a.h >= 8 && !getenv("DCTC_TC_NO_TENSORMAP") && (fstride & 15) == 0 && fstride >= a.pitch && a.pitch < (1ull << 40) &&
