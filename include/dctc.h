@@ -63,7 +63,7 @@ enum {
     DCTC_KERNEL_FP32_TILE = 1,   /* generic shared-memory tile kernel, all block sizes */
     DCTC_KERNEL_FP32_MARCH = 2,  /* b=8 register-sliding column march */
     DCTC_KERNEL_TC_SPLIT = 3,    /* tcgen05 Toeplitz GEMM, fp16 hi/lo split operands, fp32 accumulate (b = 8; b = 16 by default) */
-    DCTC_KERNEL_FP32_STREAM = 4  /* b=2, 4 streaming register-march kernel (the default for b = 2) */
+    DCTC_KERNEL_FP32_STREAM = 4  /* b=2, 4 streaming register-march kernel (what AUTO picks for them on aligned 1- or 3-channel rows) */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------------- */
