@@ -204,6 +204,44 @@ def test_stream_kernel_small_blocks(ctx, b, wts, case):
     check_with_flips(got, img, b, *wts)
 
 
+@pytest.mark.parametrize("b", [2, 4])
+@pytest.mark.parametrize("w,out_pitch,odd_base", [(272, 275, 0), (272, 272, 1), (300, 300, 0), (259, 260, 0)])
+def test_stream_kernel_output_layouts(ctx, b, w, out_pitch, odd_base):
+    """The streaming kernel writes one 64-bit value per thread and row when the output rows are 8-byte aligned, and two
+    predicated 32-bit values otherwise (odd output pitch, output pointer on an odd float, last column pair of an odd
+    width, strips that stick out of the image): every layout gives the same map, and nothing outside it is written."""
+    ch, h, n = 1, 21, 2
+    pitch = (w * ch + 15) // 16 * 16
+    imgs = np.zeros((n, h, pitch), np.uint8)
+    for f in range(n):
+        imgs[f, :, :w] = ol.synth_image(w, h, ch, 500 + b, 0, frame=f).reshape(h, w)
+    ctx.set_params(b, 0.5, 0.5)
+    d_img = ctx.dev_alloc(imgs.nbytes)
+    ctx.h2d(d_img, imgs)
+    ofs = h * out_pitch + 3                      # floats between output frames (odd or even as it comes)
+    total = n * ofs + 8
+    d_out = ctx.dev_alloc(total * 4)
+    sentinel = np.full(total, -7.0, np.float32)
+    ctx.h2d(d_out, sentinel)
+    ctx.set_kernel(dc.KERNEL_FP32_STREAM)
+    ctx.energy_batch_dev(d_img, n, h * pitch, w, h, ch, pitch, d_out + 4 * odd_base, ofs, out_pitch, sync=True)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    got = np.empty(total, np.float32)
+    ctx.d2h(got, d_out)
+    ctx.dev_free(d_img)
+    ctx.dev_free(d_out)
+    written = np.zeros(total, bool)
+    for f in range(n):
+        ctx.set_kernel(dc.KERNEL_FP32_TILE)
+        want = ctx.energy_full(np.ascontiguousarray(imgs[f, :, :w]).reshape(h, w, 1))
+        ctx.set_kernel(dc.KERNEL_AUTO)
+        for y in range(h):
+            o = odd_base + f * ofs + y * out_pitch
+            assert np.array_equal(got[o:o + w].view(np.uint32), want[y].view(np.uint32)), (f, y)
+            written[o:o + w] = True
+    assert np.all(got[~written] == -7.0)
+
+
 @pytest.mark.parametrize("b", [2, 4, 8])
 def test_stream_kernel_selector(ctx, b):
     """dctc_set_kernel(DCTC_KERNEL_FP32_STREAM) names the streaming kernel of block sizes 2 and 4 explicitly (it is also what
