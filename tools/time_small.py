@@ -5,6 +5,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import dct_carver_b200 as dc  # noqa: E402
+if os.environ.get("DCTC_LIB"):
+    dc.LIB_PATH = os.environ["DCTC_LIB"]
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 F = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 10
