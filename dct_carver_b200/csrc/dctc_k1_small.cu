@@ -325,11 +325,9 @@ __device__ __forceinline__ void step(float2 (&H)[B][B], const float* __restrict_
     }
 }
 
-#ifndef DCTC_SMALL_B4_CTAS
-#define DCTC_SMALL_B4_CTAS 5
-#endif
+// six CTAs per SM for both block sizes (b=4: 80 registers, 19.0 -> 18.3 us per 4K frame against five CTAs at 96 registers)
 template <int B, bool UNIFORM, int CH>
-__global__ void __launch_bounds__(NT, B == 2 ? 6 : DCTC_SMALL_B4_CTAS) dctc_k1_small_kernel(const DctcK1Args a, int seg_rows, int vec_ok)
+__global__ void __launch_bounds__(NT, 6) dctc_k1_small_kernel(const DctcK1Args a, int seg_rows, int vec_ok)
 {
     using G = RawGeom<CH>;
     constexpr int R0 = B / 2 - 1, R1 = B / 2;
