@@ -406,7 +406,9 @@ cudaError_t launch_small(const DctcK1Args& a, int n_frames, bool uniform, int sm
 {
     const int strips = (a.w + MW - 1) / MW;
     // segment height: long segments amortise the prologue, short ones fill the machine for small inputs
-    int seg = 128;
+    // (measured on 64 / 16 frames of 4K per launch: b=2 64 rows 9.2 / 9.6 us per frame, 128 rows 9.3 / 9.8, 256 rows 9.6 / 9.8;
+    //  b=4 64 rows 18.5 / 19.0, 128 rows 18.3 / 19.2, 256 rows 18.6 / 19.2)
+    int seg = B == 2 ? 64 : 128;
     while (seg > 16 && (long long) strips * ((a.h + seg - 1) / seg) * n_frames < 16LL * sm_count) seg >>= 1;
     const int segs = (a.h + seg - 1) / seg;
     if (segs > 65535 || n_frames > 65535) return cudaErrorInvalidConfiguration;
