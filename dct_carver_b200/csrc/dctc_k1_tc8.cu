@@ -167,10 +167,6 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
 
-__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, uint32_t r0, uint32_t r1)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
-}
 // 64 consecutive TMEM columns -> registers as two 32-column loads and one wait (a single .x64 needs 82 registers at its
 // point of issue, which ptxas checks against the launch-time register target, not the setmaxnreg value of the region)
 __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
