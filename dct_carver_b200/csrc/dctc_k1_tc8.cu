@@ -35,6 +35,9 @@
 #include "dctc_launch.h"
 #include "dctc_tc_tables.cuh"
 
+#ifndef DCTC_TC_ABL
+#define DCTC_TC_ABL 0   // timing ablations only (wrong results): 1 fold one row of eight, 2 no x-pass / split
+#endif
 namespace {
 
 // -DDCTC_TC_TIMING: per-role wait-cycle accounting (clock64), printed by CTA 0 when it retires (tools/time_tc.py)
@@ -369,9 +372,14 @@ __device__ __forceinline__ void produce_group(TcSmem& s, int g, int tid, uint32_
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = Lg[p][tid + j + 1];
         if (p == 3) bar_lfree_arrive(g & 1);   // last read of this luma buffer
+#if DCTC_TC_ABL & 2
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) { hi[k1][p] = __float_as_uint(v[k1].x); lo[k1][p] = __float_as_uint(v[k1].y); }
+#else
         dct8_fwd2_scaled(v, X);
 #pragma unroll
         for (int k1 = 0; k1 < 8; k1++) split_pair(X[k1], hi[k1][p], lo[k1][p]);
+#endif
     }
     // slot g&1 still holds group g-2, read by the MMAs of step g-2: the k1 = 0..3 operands are released when the first
     // half of those MMAs has completed, the rest at the end of the step
@@ -417,7 +425,11 @@ struct TcFold<true> {   // edges == textures: only the maximum matters
     __device__ __forceinline__ void add(const uint32_t (&v)[64])
     {
 #pragma unroll
+#if DCTC_TC_ABL & 1
+        for (int i = 0; i < 1; i++) {
+#else
         for (int i = 0; i < 8; i++) {
+#endif
             float t = m[i];
             if (K1 != 0) t = fmaxf(t, fabsf(__uint_as_float(v[tc_col(i, 0)])));   // (0,0) is skipped (src/dct.c:101)
             t = fmaxf(t, fabsf(__uint_as_float(v[tc_col(i, 1)])));
