@@ -1,7 +1,6 @@
 // C ABI of the DCT-Carver energy hot path (see include/dctc.h for the reference interface each entry replaces).
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "dctc_common.cuh"
@@ -189,7 +188,7 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
     case DCTC_KERNEL_FP32_MARCH: e = dctc_launch_k1_march8(a, n_frames, uniform, stream); break;
     case DCTC_KERNEL_TC_SPLIT:
         // every launch takes its own work-item counter, so launches in flight on different streams never share one
-        e = (getenv("DCTC_TC_WIDE") ? dctc_launch_k1_tc8w : dctc_launch_k1_tc8)(a, n_frames, uniform, ctx->tc_counters + (ctx->tc_next++ % DCTC_TC_COUNTERS), ctx->sm_count, stream);
+        e = dctc_launch_k1_tc8(a, n_frames, uniform, ctx->tc_counters + (ctx->tc_next++ % DCTC_TC_COUNTERS), ctx->sm_count, stream);
         // outside the tensor-core fast path (channel count / alignment): same operator on the FP32 march kernel
         if (e == cudaErrorNotSupported) e = dctc_launch_k1_march8(a, n_frames, uniform, stream);
         break;
