@@ -44,10 +44,10 @@ WORKLOADS = {
 
 def kernel_name(blocksize, kernel):
     if blocksize == 8:
-        return {0: "dctc_k1_tc8_kernel (tcgen05 y-pass)", 3: "dctc_k1_tc8_kernel (tcgen05 y-pass)",
+        return {0: "dctc_k1_tc8_kernel (tcgen05 y-pass, TMA-staged raw tiles)", 3: "dctc_k1_tc8_kernel (tcgen05 y-pass, TMA-staged raw tiles)",
                 2: "dctc_k1_march8_kernel (FP32x2 register march)"}.get(kernel, "dctc_k1_tile_kernel (FP32)")
     if blocksize in (2, 4) and kernel == 0:
-        return "dctc_k1_small_kernel (FP32 streaming register march)"
+        return "dctc_k1_small_kernel (FP32x2 streaming register march, two columns per thread)"
     if blocksize == 16 and kernel in (0, 3):
         return "dctc_k1_tc16_kernel (tcgen05 y-pass)"
     return "dctc_k1_tile_kernel (FP32)"
@@ -63,11 +63,12 @@ def arithmetic(blocksize, kernel):
 def kernel_note(blocksize):
     base = "traffic = DRAM bytes per launch from ncu (profiles/traffic.json); "
     if blocksize == 8:
-        return base + ("blocksize 8 is compute-bound (24 tcgen05 MMAs + 32 FMNMX3 per 8x128 px), not HBM-bound: "
+        return base + ("blocksize 8 is compute-bound (24 tcgen05 MMAs per 8x128 px + 32 FMNMX3 and 35 x-pass / split instructions per px), not HBM-bound: "
                        "see DESIGN.md section 4")
     if blocksize in (2, 4):
-        return base + "blocksize %d: HBM / instruction-issue bound streaming kernel, see DESIGN.md section 4" % blocksize
-    return base + ("blocksize 16 is tensor-bound (96 tcgen05 MMAs M128 N128 K16 per 16x64 px: floor ~183 us per 4K frame), "
+        return base + ("blocksize 2: HBM-bound streaming kernel, see DESIGN.md section 4" if blocksize == 2 else
+                       "blocksize 4: FP32-pipe-bound streaming kernel (56 FP32 lane-operations per pixel), see DESIGN.md section 4")
+    return base + ("blocksize 16 is tensor-bound (96 tcgen05 MMAs M128 N128/112 K16 per 16x64 px: floor ~175 us per 4K frame), "
                    "not HBM-bound: see DESIGN.md section 4")
 
 
