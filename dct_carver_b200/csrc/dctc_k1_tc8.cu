@@ -8,7 +8,7 @@
 //       lies inside the image is ONE 3-D tensor copy (TMA, cp.async.bulk.tensor.3d over (row bytes / 4, rows, frames),
 //       completion on the buffer's mbarrier); groups that touch the top / bottom edge or the halo rows of a band (edge
 //       replication, src/render.c:122-132) are gathered row by row with 16-byte cp.async.  Then convert one group to luma
-//       (four pixels x two rows per task: 32-bit shared loads, PRMT + FADD byte->float, no XU-pipe conversions) and
+//       (four pixels x two rows per task: 32-bit shared loads, exact integer luma by dp2a, four I2F) and
 //       hand the luma row pairs to the producers through hardware named barriers (double-buffered)
 //   producer warps 0-3 (thread = column): run the
 //       x-pass (one packed FP32x2 DCT-8 per row pair), split each coefficient H[k1] into fp16 hi + fp16 lo
@@ -25,8 +25,9 @@
 //   consumer warps 4-7 (thread = column): tcgen05.ld the 64 accumulators of (8 rows x 8 k2), fold |.|-max over k2
 //       and k1 with FMNMX3 (or the last-arg-max class tracker when edges != textures), scale, coalesced store.
 //
-// Per pixel the CUDA cores execute ~100 instructions instead of the ~264 of the FP32 march kernel; the tensor pipe
-// does 24 M128 N64 K16 MMAs per 1024 pixels (36.3 clk each measured, profiles/r01_tcgen05_probe2.txt).
+// Per pixel the CUDA cores execute ~120 instructions instead of the ~264 of the FP32 march kernel; the tensor pipe
+// does 24 M128 K16 MMAs per 1024 pixels (16 with N = 64: 36.3 clk each measured, profiles/r01_tcgen05_probe2.txt; 8 with
+// N = 48).  The operands of a group are announced in two halves (k1 = 0..3, 4..7).
 #include <cuda.h>       // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_fp16.h>
 #include <cstdio>
