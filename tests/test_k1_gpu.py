@@ -204,6 +204,36 @@ def test_stream_kernel_small_blocks(ctx, b, wts, case):
     check_with_flips(got, img, b, *wts)
 
 
+@pytest.mark.parametrize("b", [8, 16, 4])
+def test_batch_with_row_and_frame_padding(ctx, b):
+    """Frames with a row pitch larger than the row and a frame stride larger than the frame (both 16-byte multiples, so
+    every kernel stays on its fast path; block size 8 stages its raw tiles through a 3-D tensor map built from exactly
+    these strides): each frame of the batch equals the same frame computed alone from a tight buffer."""
+    n, w, h, ch = 3, 200, 77, 3
+    pitch = (w * ch + 15) // 16 * 16 + 32
+    fs = h * pitch + 4096
+    buf = np.full(n * fs, 0xEE, np.uint8)                      # padding bytes must not matter
+    frames = [ol.synth_image(w, h, ch, 700 + b, 0, frame=f) for f in range(n)]
+    for f in range(n):
+        v = buf[f * fs:f * fs + h * pitch].reshape(h, pitch)
+        v[:, :w * ch] = frames[f].reshape(h, w * ch)
+    ctx.set_params(b, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    d_img = ctx.dev_alloc(buf.nbytes)
+    ctx.h2d(d_img, buf)
+    ofs = w * h + 64
+    d_out = ctx.dev_alloc(n * ofs * 4)
+    ctx.energy_batch_dev(d_img, n, fs, w, h, ch, pitch, d_out, ofs, w, sync=True)
+    got = np.empty(n * ofs, np.float32)
+    ctx.d2h(got, d_out)
+    ctx.dev_free(d_img)
+    ctx.dev_free(d_out)
+    for f in range(n):
+        want = ctx.energy_full(frames[f])
+        assert np.array_equal(got[f * ofs:f * ofs + w * h].reshape(h, w).view(np.uint32), want.view(np.uint32)), f
+        ol.assert_parity(want, ol.best_energy(frames[f], b, 0.5, 0.5))
+
+
 @pytest.mark.parametrize("b", [2, 4])
 @pytest.mark.parametrize("w,out_pitch,odd_base", [(272, 275, 0), (272, 272, 1), (300, 300, 0), (259, 260, 0)])
 def test_stream_kernel_output_layouts(ctx, b, w, out_pitch, odd_base):
