@@ -442,7 +442,8 @@ def main():
     e2e = None
     if not args.no_e2e and args.workload != "gigapixel":
         Fe = min(F, 32)
-        h_in = dc.pinned_array((Fe, h, w, ch), np.uint8)
+        wc = os.environ.get("DCTC_E2E_WC", "0") != "0"      # input frames in write-combined pinned memory (no measurable effect)
+        h_in = dc.pinned_array((Fe, h, w, ch), np.uint8, write_combined=wc)
         h_out = dc.pinned_array((Fe, h, w), np.float32)
         tmp = np.empty((h, w, ch), np.uint8)
         for f in range(Fe):
@@ -462,11 +463,12 @@ def main():
             te = float(t.item())
         e2e = {"value": Fe * w * h * world / te / 1e6, "unit": UNIT, "h2d_bytes_per_step": Fe * h * w * ch * world,
                "d2h_bytes_per_step": Fe * h * w * 4 * world, "frames_per_step": Fe * world, "steps_timed": ke,
-               "api": "dctc_energy_batch (host buffers, 4-slot H2D/compute/D2H overlap)"}
+               "api": "dctc_energy_batch (host buffers, 4-slot H2D/compute/D2H overlap)",
+               "host_buffers": "pinned; input frames " + ("write-combined" if wc else "cacheable")}
         assert float(np.abs(h_out[0]).max()) > 0.0
         # the ceiling of that path: pinned-copy bandwidth with every rank copying at the same time
         barrier()
-        pc = ctx.pcie_probe(256 << 20, 6)
+        pc = ctx.pcie_probe(int(os.environ.get("DCTC_PROBE_BYTES", 256 << 20)), int(os.environ.get("DCTC_PROBE_ITERS", 6)))
         barrier()
         if dist is not None:
             t = torch.tensor([pc["h2d_gbs"], pc["d2h_gbs"], pc["bidir_gbs_per_dir"]], device="cuda", dtype=torch.float64)

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "dctc_energy_minmax_dev", "dctc_energy_image_dev", "dctc_carver_energy_image", "dctc_preview_energy",
     "dctc_carver_set_dump_vmaps", "dctc_carver_vmap", "dctc_carver_paint_seams",
     "dctc_synth_fill_dev", "dctc_synth_byte", "dctc_ipc_export", "dctc_ipc_open", "dctc_ipc_close",
-    "dctc_dev_alloc", "dctc_dev_free", "dctc_host_alloc_pinned", "dctc_host_free_pinned", "dctc_memcpy_h2d",
+    "dctc_dev_alloc", "dctc_dev_free", "dctc_host_alloc_pinned", "dctc_host_alloc_pinned_wc", "dctc_host_free_pinned", "dctc_memcpy_h2d",
     "dctc_memcpy_d2h", "dctc_memset_dev", "dctc_sync", "dctc_timer_begin", "dctc_timer_end",
     # multi-GPU host layer (csrc/dctc_multi.cu)
     "dctc_band_plan", "dctc_multi_create", "dctc_multi_destroy", "dctc_multi_device_count", "dctc_multi_context",
@@ -118,6 +118,7 @@ def lib():
         "dctc_dev_alloc": (i32, [vp, C.POINTER(vp), sz]),
         "dctc_dev_free": (i32, [vp, vp]),
         "dctc_host_alloc_pinned": (i32, [C.POINTER(vp), sz]),
+        "dctc_host_alloc_pinned_wc": (i32, [C.POINTER(vp), sz]),
         "dctc_host_free_pinned": (i32, [vp]),
         "dctc_memcpy_h2d": (i32, [vp, vp, vp, sz]),
         "dctc_memcpy_d2h": (i32, [vp, vp, vp, sz]),
@@ -175,12 +176,16 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def pinned_array(shape, dtype):
-    """numpy array over cudaMallocHost memory (kept alive by the returned array's base)."""
+def pinned_array(shape, dtype, write_combined=False):
+    """numpy array over cudaMallocHost memory (kept alive by the returned array's base); write_combined: for input frames
+    the host only writes."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     p = C.c_void_p()
-    _check(lib().dctc_host_alloc_pinned(C.byref(p), n), "dctc_host_alloc_pinned")
+    if write_combined:
+        _check(lib().dctc_host_alloc_pinned_wc(C.byref(p), n), "dctc_host_alloc_pinned_wc")
+    else:
+        _check(lib().dctc_host_alloc_pinned(C.byref(p), n), "dctc_host_alloc_pinned")
     buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     _PINNED[id(buf)] = (buf, p.value)

@@ -415,6 +415,14 @@ int dctc_host_alloc_pinned(void** h_ptr, size_t bytes)
     return e == cudaSuccess ? DCTC_OK : dctc_fail_cuda(nullptr, e);
 }
 
+int dctc_host_alloc_pinned_wc(void** h_ptr, size_t bytes)
+{
+    if (!h_ptr) return DCTC_ERR_INVALID;
+    *h_ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocWriteCombined);
+    return e == cudaSuccess ? DCTC_OK : dctc_fail_cuda(nullptr, e);
+}
+
 int dctc_host_free_pinned(void* h_ptr)
 {
     cudaError_t e = cudaFreeHost(h_ptr);

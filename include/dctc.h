@@ -315,6 +315,9 @@ int dctc_pcie_probe(dctc_context *ctx, size_t bytes, int iters, double *h2d_gbs,
 int dctc_dev_alloc(dctc_context *ctx, void **d_ptr, size_t bytes);
 int dctc_dev_free(dctc_context *ctx, void *d_ptr);
 int dctc_host_alloc_pinned(void **h_ptr, size_t bytes);
+/* write-combined pinned memory for INPUT frames the host only writes (uploads do not snoop the CPU caches; CPU reads of
+ * such memory are slow); freed with dctc_host_free_pinned */
+int dctc_host_alloc_pinned_wc(void **h_ptr, size_t bytes);
 int dctc_host_free_pinned(void *h_ptr);
 int dctc_memcpy_h2d(dctc_context *ctx, void *d_dst, const void *h_src, size_t bytes);
 int dctc_memcpy_d2h(dctc_context *ctx, void *h_dst, const void *d_src, size_t bytes);
