@@ -495,6 +495,9 @@ def main():
                 burst = frames_config(ctx, timer, w, h, ch, F, 16, 20, hbm_peak, SEED, d_in=d_in, d_out=d_out)
                 burst["clocks"] = bs.stop()
                 configs["C2_burst_16_frames"] = burst
+                # same, 64 frames per launch (5 launches = 14 ms): the tail of the persistent item loop weighs less
+                time.sleep(0.3)
+                configs["C2_burst_64_frames"] = frames_config(ctx, timer, w, h, ch, F, 64, 5, hbm_peak, SEED, d_in=d_in, d_out=d_out)
                 configs["C2_one_frame_per_launch"] = frames_config(ctx, timer, w, h, ch, F, 1, 200, hbm_peak, SEED, d_in=d_in, d_out=d_out)
                 ctx.set_params(8, 0.8, 0.2)
                 configs["C2_weights_0.8_0.2"] = frames_config(ctx, timer, w, h, ch, F, 64, 5, hbm_peak, SEED, d_in=d_in, d_out=d_out)
