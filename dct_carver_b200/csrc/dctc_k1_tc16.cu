@@ -348,6 +348,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
+    // programmatic dependent launch, as in dctc_k1_tc8.cu: this launch's ramp (TMEM allocation, Toeplitz operands from
+    // immutable tables) overlaps the tail of the grid before it in the stream
+    asm volatile("griddepcontrol.launch_dependents;");
     if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -366,6 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dctc_k1_tc16_kernel(const DctcK1A
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // everything before this grid in the stream is complete and visible
     const uint32_t lane_off = (uint32_t) ((warp & 3) * 32) << 16;
 
     auto begin_item = [&](bool first) -> int {
@@ -605,7 +609,8 @@ cudaError_t dctc_launch_k1_tc16(const DctcK1Args& a, int n_frames, bool uniform,
     do {                                                                                                               \
         cudaError_t ea = cudaFuncSetAttribute(dctc_k1_tc16_kernel<U, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (ea != cudaSuccess) return ea;                                                                              \
-        dctc_k1_tc16_kernel<U, C><<<grid, NTHREADS, smem, stream>>>(a, seg, strips, segs, (int) items, phase, counter); \
+        ea = dctc_launch_pdl(dctc_k1_tc16_kernel<U, C>, dim3(grid), dim3(NTHREADS), (size_t) smem, stream, true, a, seg, strips, segs, (int) items, phase, counter); \
+        if (ea != cudaSuccess) return ea;                                                                              \
     } while (0)
     if (a.channels == 3) { if (uniform) DCTC16_LAUNCH(true, 3); else DCTC16_LAUNCH(false, 3); }
     else { if (uniform) DCTC16_LAUNCH(true, 1); else DCTC16_LAUNCH(false, 1); }

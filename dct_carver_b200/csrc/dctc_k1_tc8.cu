@@ -525,6 +525,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
+    // Programmatic dependent launch: the next launch in the stream may start its CTAs as soon as this grid's CTAs retire;
+    // what follows up to griddepcontrol.wait (TMEM allocation, the Toeplitz operands from immutable tables) touches no
+    // memory an earlier grid writes, so a launch's ramp overlaps its predecessor's tail.
+    asm volatile("griddepcontrol.launch_dependents;");
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -541,6 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // everything before this grid in the stream is complete and visible
     const uint32_t lane_off = (uint32_t) ((warp & 3) * 32) << 16;
 
     // Every role runs its own copy of the persistent item loop (begin_item / end_item contain the CTA-wide barriers), so
@@ -843,7 +848,8 @@ cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, 
     do {                                                                                                               \
         cudaError_t ea = cudaFuncSetAttribute(dctc_k1_tc8_kernel<U, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAD_SMEM); \
         if (ea != cudaSuccess) return ea;                                                                              \
-        dctc_k1_tc8_kernel<U, C><<<grid, NTHREADS, PAD_SMEM, stream>>>(a, seg, strips, segs, (int) items, counter, tmap, use_tmap); \
+        ea = dctc_launch_pdl(dctc_k1_tc8_kernel<U, C>, dim3(grid), dim3(NTHREADS), PAD_SMEM, stream, true, a, seg, strips, segs, (int) items, counter, tmap, use_tmap); \
+        if (ea != cudaSuccess) return ea;                                                                              \
     } while (0)
     if (a.channels == 3) { if (uniform) DCTC_TC_LAUNCH(true, 3); else DCTC_TC_LAUNCH(false, 3); }
     else { if (uniform) DCTC_TC_LAUNCH(true, 1); else DCTC_TC_LAUNCH(false, 1); }
