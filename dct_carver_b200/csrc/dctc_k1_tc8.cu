@@ -76,7 +76,6 @@ struct alignas(128) TcSmem {
     __half B[4][64 * 16];            // Tz as UMMA K-major no-swizzle operands: [0] Bh, [1] Bl, [2]/[3] the K-swapped copies
     float2 L[2][4][LWP];             // luma of two groups: [buffer][row pair][column], .x = even row
     uint8_t Raw[3][8 * RawGeom<3>::ROW];
-    float park[16][MW];              // non-uniform weights: per-row quantities of the class rule parked by the consumers
     uint64_t bar_a_free, bar_a_free_lo, bar_d_full[2];
     uint64_t bar_raw[3];             // raw buffer filled: NCONV arrivals (+ the bytes of a tensor copy)
     uint32_t tmem_base;
@@ -441,21 +440,17 @@ struct TcFold<true> {   // edges == textures: only the maximum matters
         }
     }
     __device__ __forceinline__ float result(int i, float we, float wt) const { (void) we; return m[i] * wt; }
-    __device__ __forceinline__ void set_park(float*) {}
 };
 
 template <>
 struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
     // With A = |T[0][1]|, M = max|T[0][2..]|, Bv = |T[1][0]|, Z = max of the rest, the winner is a texture atom iff
     //   Z >= max(A, M, Bv)  or  (Bv < max(A, M) and M >= A).
-    // A and M are final after the k1 = 0 tile, Bv after the k1 = 1 tile: max(A, M), the bit (M >= A) and Bv are parked
-    // (shared memory / one flag register) so that the six remaining tiles fold with the register budget of the
-    // uniform case (64 accumulator registers + 8 maxima) -- keeping all four quantities of all eight rows in
-    // registers spilled 1.2 KB per thread and made this variant four times slower than the uniform one.
-    float z[8];
-    unsigned flags;          // bit i: M >= A in row i
-    float* park;             // park[(which * 8 + i) * MW]: which = 0 max(A, M), 1 Bv; this thread's column
-    __device__ __forceinline__ void set_park(float* p) { park = p; }
+    // A and M are final after the k1 = 0 tile, Bv arrives first in the k1 = 1 tile; from then on only
+    //   pre = max(A, M, Bv)  and the bit  tex_pre = (Bv < max(A, M) and M >= A)
+    // are needed next to the running Z:  texture iff  Z >= pre  or  tex_pre.
+    float z[8], pre[8];
+    unsigned flags;          // bit i: M >= A (after the k1 = 0 tile), then tex_pre (after the k1 = 1 tile) of row i
     __device__ __forceinline__ void init()
     {
 #pragma unroll
@@ -472,11 +467,16 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
                 float mm = -1.0f;
 #pragma unroll
                 for (int k2 = 2; k2 < 8; k2++) mm = fmaxf(mm, fabsf(__uint_as_float(v[tc_col(i, k2)])));
-                park[i * MW] = fmaxf(a, mm);
+                pre[i] = fmaxf(a, mm);
                 if (mm >= a) flags |= 1u << i;
             } else {
-                if (K1 == 1) park[(8 + i) * MW] = fabsf(__uint_as_float(v[tc_col(i, 0)]));
-                else z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[tc_col(i, 0)])));
+                if (K1 == 1) {
+                    const float bv = fabsf(__uint_as_float(v[tc_col(i, 0)]));
+                    if (bv >= pre[i]) flags &= ~(1u << i);      // Bv is the last maximal index among A, M, Bv: an edge atom
+                    pre[i] = fmaxf(pre[i], bv);
+                } else {
+                    z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[tc_col(i, 0)])));
+                }
 #pragma unroll
                 for (int k2 = 1; k2 < 8; k2++) z[i] = fmaxf(z[i], fabsf(__uint_as_float(v[tc_col(i, k2)])));
             }
@@ -484,9 +484,8 @@ struct TcFold<false> {  // last-arg-max class rule of DctcTracker<false>
     }
     __device__ __forceinline__ float result(int i, float we, float wt) const
     {
-        const float am = park[i * MW], bv = park[(8 + i) * MW];
-        const float top = fmaxf(fmaxf(am, bv), z[i]);
-        const bool tex = (z[i] >= fmaxf(am, bv)) || (!(bv >= am) && ((flags >> i) & 1u));
+        const float top = fmaxf(pre[i], z[i]);
+        const bool tex = (z[i] >= pre[i]) || ((flags >> i) & 1u);
         return top * (tex ? wt : we);
     }
 };
@@ -628,7 +627,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) dctc_k1_tc8_kernel(const DctcK1Ar
         for (int st = 0; st < nsteps; st++) {
             TcFold<UNIFORM> f;
             f.init();
-            f.set_park(&s.park[0][px]);
             bar_step_sync();                                  // the MMA warp has started this step
             consume_k1<0, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
             consume_k1<1, UNIFORM>(s, f, tmem_lane, lane0, g_tt_acc);
