@@ -204,6 +204,35 @@ def test_stream_kernel_small_blocks(ctx, b, wts, case):
     check_with_flips(got, img, b, *wts)
 
 
+@pytest.mark.parametrize("b", [8, 16])
+def test_back_to_back_launches_are_ordered(ctx, b):
+    """The tensor-core launches are chained by programmatic dependent launches (the ramp of a launch overlaps the tail of
+    its predecessor).  A launch whose INPUT is the previous launch's OUTPUT (the float map read as a grey image four
+    times as wide) must still see the complete map: same result as with a host synchronisation in between."""
+    w, h = 512, 270
+    img = ol.synth_image(w, h, 1, 4242, 0)
+    ctx.set_params(b, 0.5, 0.5)
+    ctx.set_kernel(dc.KERNEL_AUTO)
+    d_img = ctx.dev_alloc(w * h)
+    ctx.h2d(d_img, img)
+    d_mid = ctx.dev_alloc(w * h * 4)
+    d_out = ctx.dev_alloc(4 * w * h * 4)
+    res = []
+    for sync_between in (False, True):
+        ctx.h2d(d_mid, np.zeros(w * h, np.float32))
+        for _ in range(3):                                    # keep the stream busy so that launches really follow each other
+            ctx.energy_batch_dev(d_img, 1, 0, w, h, 1, w, d_mid, 0, w, sync=sync_between)
+            ctx.energy_batch_dev(d_mid, 1, 0, 4 * w, h, 1, 4 * w, d_out, 0, 4 * w, sync=sync_between)
+        ctx.sync()
+        got = np.empty((h, 4 * w), np.float32)
+        ctx.d2h(got, d_out)
+        res.append(got)
+    for d in (d_img, d_mid, d_out):
+        ctx.dev_free(d)
+    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
+    assert float(np.abs(res[0]).max()) > 0.0
+
+
 @pytest.mark.parametrize("b", [8, 16, 4])
 def test_batch_with_row_and_frame_padding(ctx, b):
     """Frames with a row pitch larger than the row and a frame stride larger than the frame (both 16-byte multiples, so
