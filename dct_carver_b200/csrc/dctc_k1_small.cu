@@ -329,6 +329,9 @@ __device__ __forceinline__ void step(float2 (&H)[B][B], const float* __restrict_
 template <int B, bool UNIFORM, int CH>
 __global__ void __launch_bounds__(NT, 6) dctc_k1_small_kernel(const DctcK1Args a, int seg_rows, int vec_ok)
 {
+    // programmatic dependent launch: back-to-back launches hide each other's launch latency; nothing is read or written
+    // before the predecessor in the stream has completed
+    DCTC_PDL_PROLOGUE();
     using G = RawGeom<CH>;
     constexpr int R0 = B / 2 - 1, R1 = B / 2;
     __shared__ __align__(16) float L[2][8 * LWP];
@@ -415,7 +418,11 @@ cudaError_t launch_small(const DctcK1Args& a, int n_frames, bool uniform, int sm
     // 64-bit stores need 8-byte aligned output rows
     const int vec_ok = (((uintptr_t) a.out & 7) == 0 && (a.out_pitch & 1) == 0 && (a.out_frame_stride & 1) == 0) ? 1 : 0;
     dim3 grid(strips, segs, n_frames), block(NT);
-#define DCTC_SMALL_LAUNCH(U, C) dctc_k1_small_kernel<B, U, C><<<grid, block, 0, stream>>>(a, seg, vec_ok)
+#define DCTC_SMALL_LAUNCH(U, C)                                                                                        \
+    do {                                                                                                               \
+        cudaError_t el = dctc_launch_pdl(dctc_k1_small_kernel<B, U, C>, grid, block, 0, stream, true, a, seg, vec_ok); \
+        if (el != cudaSuccess) return el;                                                                              \
+    } while (0)
     if (a.channels == 3) { if (uniform) DCTC_SMALL_LAUNCH(true, 3); else DCTC_SMALL_LAUNCH(false, 3); }
     else { if (uniform) DCTC_SMALL_LAUNCH(true, 1); else DCTC_SMALL_LAUNCH(false, 1); }
 #undef DCTC_SMALL_LAUNCH
