@@ -176,10 +176,7 @@ int dctc_run_k1(dctc_context* ctx, DctcK1Args& a, int n_frames, cudaStream_t str
         // block sizes 2 and 4 (HBM-bound): full maps stream through the register-march kernel unless the tile kernel was
         // asked for explicitly; both produce bit-identical maps
         e = cudaErrorNotSupported;
-        // block size 4 (FP32-pipe-bound on the CUDA cores): full maps run their y-pass on the tensor cores
-        if ((ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_TC_SPLIT) && !a.seam && !a.preview && ctx->blocksize == 4)
-            e = dctc_launch_k1_tc4(a, n_frames, uniform, ctx->sm_count, stream);
-        if (e == cudaErrorNotSupported && (ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_FP32_STREAM) && !a.seam && !a.preview &&
+        if ((ctx->kernel == DCTC_KERNEL_AUTO || ctx->kernel == DCTC_KERNEL_FP32_STREAM) && !a.seam && !a.preview &&
             (ctx->blocksize == 2 || ctx->blocksize == 4))
             e = dctc_launch_k1_small(a, ctx->blocksize, n_frames, uniform, ctx->sm_count, stream);
         // block size 16 (compute-bound): full maps run their y-pass on the tensor cores unless the FP32 tile kernel was

@@ -41,7 +41,6 @@ cudaError_t dctc_launch_k1_tile(const DctcK1Args& a, int blocksize, int n_frames
 cudaError_t dctc_launch_k1_small(const DctcK1Args& a, int blocksize, int n_frames, bool uniform, int sm_count, cudaStream_t stream);
 cudaError_t dctc_launch_k1_march8(const DctcK1Args& a, int n_frames, bool uniform, cudaStream_t stream);
 cudaError_t dctc_launch_k1_tc8(const DctcK1Args& a, int n_frames, bool uniform, int* counter, int sm_count, cudaStream_t stream);
-cudaError_t dctc_launch_k1_tc4(const DctcK1Args& a, int n_frames, bool uniform, int sm_count, cudaStream_t stream);
 cudaError_t dctc_launch_k1_tc16(const DctcK1Args& a, int n_frames, bool uniform, int* counter, int sm_count, cudaStream_t stream);
 cudaError_t dctc_launch_synth(uint8_t* d_img, int n_frames, size_t frame_stride, int w, int h, int channels,
                               size_t pitch, uint32_t seed, int pattern, int first_frame, int y_offset,
